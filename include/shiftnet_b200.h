@@ -1,0 +1,147 @@
+/*
+ * shiftnet_b200 -- C-ABI of the B200-native (sm_100a) Shift-Net forward hot path.
+ *
+ * The reference (dasongli1/Shift-Net) has no FFI/operator layer of its own: its boundary is the
+ * Python class ``basicsr.models.archs.gshift_*.GShiftNet``.  The entry
+ * points below are what a Python/ctypes (or cgo/JNI) binding of that class's forward would bind;
+ * each cites the reference code it replaces (paths relative to
+ * /root/reference/basicsr/models/archs/, "d2" = gshift_deblur2.py).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer (cudaMalloc'd / torch storage); nothing is owned or
+ *     freed by the library; all calls are stream-ordered and stateless (thread-safe per stream);
+ *   - activations are NHWC fp16, shape (T, H, W, Cp) with Cp = channel count padded to a multiple
+ *     of 16 (padding channels are zero and stay zero);
+ *   - return value: 0 on success, negative GSN_E_* on failure; gsn_last_error() gives the message
+ *     of the last failure on the calling thread;
+ *   - ``stream`` is a cudaStream_t passed as void*.
+ */
+#ifndef SHIFTNET_B200_H
+#define SHIFTNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSN_OK 0
+#define GSN_E_BADARG (-1)
+#define GSN_E_CUDA (-2)
+#define GSN_E_UNSUPPORTED (-3)
+
+#define GSN_DTYPE_F16 0
+#define GSN_DTYPE_F32 1
+
+int gsn_version(void);
+const char *gsn_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's "gpu_launches" evidence). */
+unsigned long long gsn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic dense convolution on tensor cores (implicit GEMM), replaces every nn.Conv2d with
+ * groups == 1 on the path: CAB bodies (d2:143-158), conv_trans (d2:713), DownSample (d2:333-343),
+ * down01 (d2:551), SkipUpSample's 1x1 (d2:344-353, applied before the bilinear upsample -- both
+ * are linear), PixelShufflePack (d2:259-281, shuffle + PReLU fused into the store), rconcat
+ * (d2:727, the torch.cat of d2:739 is folded into the load of up to 3 sources), conv_hr0 (d2:572).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int T, Hin, Win, Hout, Wout;
+  int n_src;            /* 1..3 sources, concatenated along channels */
+  const void *src[3];   /* NHWC fp16 (T,Hin,Win,src_c[i]) */
+  int src_c[3];         /* padded channel count of each source (multiple of 8) */
+  int cin_p;            /* sum of src_c, multiple of 16 */
+  int cout_p;           /* padded output channels: 16, 32, 48, 64 or 80 */
+  int ks, stride, pad;  /* kernel size 1..3, stride 1..2, zero padding */
+  const void *wpack;    /* fp16 weights in mma.m16n8k16 B-fragment order: [tap][cin_p/16][cout_p/8][32 lanes][4] */
+  const float *bias;    /* cout_p floats or NULL */
+  int has_prelu;        /* apply PReLU(slope) after bias */
+  float prelu_slope;
+  const void *residual; /* NULL or NHWC fp16 (T,Hout,Wout,cout_p) added last */
+  int pixel_shuffle;    /* 1: dst is (T,2Hout,2Wout,cout_p/4), F.pixel_shuffle(.,2) fused into the store */
+  float *chan_partial;  /* NULL or [T][tiles][cout_p] fp32: per-tile channel sums of the output (for CALayer) */
+  void *dst;            /* NHWC fp16 */
+} GsnConvDesc;
+
+/* tiles per frame the conv kernel uses for chan_partial (16x16 output tiles) */
+int gsn_conv_tiles(int Hout, int Wout);
+int gsn_conv_mma(const GsnConvDesc *d, void *stream);
+
+/* First conv: NCHW user clip -> NHWC features. Replaces feat_extract[0] (d2:710), including the
+ * x[0] un-batching of d2:750 and (denoise) the torch.cat((x, noise_map)) of gshift_denoise2.py:749.
+ * x: (T,cin,H,W) fp16 or fp32; w: fp32 [9][cin][cout_p]; bias: fp32 [cout_p]; dst NHWC fp16. */
+int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, int W, const float *w, const float *bias,
+                int cout_p, void *dst, void *stream);
+
+/* Last conv: NHWC features -> NCHW frames + input residual. Replaces conv_last (d2:712,745) and the
+ * "+ shortcut[num_fb:frames-num_ff]" of d2:756.  src (T,H,W,cp) fp16; w fp32 [ks*ks][cp][3];
+ * resid/dst: (T,3,H,W) in x_dtype, resid has cres channels per frame (3, or 4 for the cat'ed denoise input). */
+int gsn_conv_out(const void *src, int cp, int ks, const float *w, const void *resid, int cres, int x_dtype, int T, int H,
+                 int W, void *dst, void *stream);
+
+/* CALayer squeeze-excite MLP (d2:54-71): s[t][c] = sigmoid(W2 relu(W1 mean_hw)), from per-tile sums.
+ * partial [T][ntiles][cp]; w1 fp32 [cr][c]; w2 fp32 [c][cr]; s fp32 [T][cp]. */
+int gsn_ca_scale(const float *partial, int ntiles, float inv_hw, const float *w1, const float *w2, int c, int cr, int cp,
+                 int T, float *s, void *stream);
+
+/* out = x + res * s[t][c] (+ extra)   -- the "res = CA(res); res += x" of CAB.forward (d2:154-158). */
+int gsn_scale_residual(const void *x, const void *res, const float *s, const void *extra, void *out, int T, long long hw,
+                       int cp, void *stream);
+
+/* dst = bilinear_x2(src) + skip   (nn.Upsample(scale_factor=2, bilinear, align_corners=False), d2:347,350-353). */
+int gsn_upsample2x_add(const void *src, const void *skip, void *dst, int T, int h, int w, int cp, void *stream);
+
+/* out = a + b (fp16, n elements, n % 8 == 0) -- the stage-level shortcuts (d2:736,744). */
+int gsn_add(const void *a, const void *b, void *out, long long n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused grouped spatial-temporal shift + NAF block (Encoder_shift_block, d2:443-530).
+ * One (shift, CAB2) or CAB1 step is two kernels around the global average pool of CALayer2:
+ *   pass A: [temporal roll + spatial shift gather -> dw3x3 (conv1) ->] LayerNorm -> 1x1 -> dw3x3+id ->
+ *           gate -> dw5x5+dw3x3+id -> 1x1 -> sigmoid gate -> z (C ch) + per-tile channel sums
+ *   fold  : CA MLP on the pooled z, folded with beta into a per-frame effective last-1x1 weight
+ *   pass B: out = shortcut + Weff_t . z      (shortcut = the ROLLED stream for CAB2, d2:253,257)
+ * ------------------------------------------------------------------------------------------- */
+#define GSN_MODE_CAB1 0
+#define GSN_MODE_CAB2_FWD 1
+#define GSN_MODE_CAB2_REV 2
+
+typedef struct {
+  int T, H, W, C;       /* C = 64 (Ours-s); activations (T,H,W,C) NHWC fp16 */
+  int mode;             /* GSN_MODE_* */
+  int circular;         /* temporal roll wraps (d2:504-505) or clamps (gshift_deblur1.py:513,517) */
+  const void *x;        /* input of the step (un-rolled previous output) */
+  const void *wblob;    /* packed pass-A weights, see host/packing.py (pack_cab_pass_a) */
+  void *z;              /* out: gated features (T,H,W,C) fp16 */
+  float *chan_partial;  /* out: [T][gsn_cab_tiles][C] fp32 per-tile channel sums of z */
+  int debug_stage;      /* 0 = normal; >0 dumps an intermediate smem stage to debug_out (tests only) */
+  void *debug_out;
+} GsnCabPassA;
+
+int gsn_cab_tiles(int mode, int H, int W);
+int gsn_cab_pass_a(const GsnCabPassA *d, void *stream);
+
+/* fold: weff[t] = diag(beta) W3 diag(s_t) as fp16 [T][C/8][C][8] (k-chunk planar), s_t from CALayer2
+ * (d2:72-89,238-239,257).  w_du0 [cr][C], w_du2 [C][cr], w3 [C][C], beta [C], bias3 [C] or NULL (fp32).
+ * beff [T][C] fp32 = beta*bias3 (zeros if bias3 == NULL). */
+int gsn_cab_fold(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,
+                 const float *w3, const float *beta, const float *bias3, int C, int T, void *weff, float *beff,
+                 void *stream);
+
+typedef struct {
+  int T, H, W, C;
+  int mode, circular;   /* shortcut = rolled x for CAB2 modes, x itself for CAB1 */
+  const void *x;        /* the same tensor pass A read */
+  const void *z;
+  const void *weff;     /* from gsn_cab_fold */
+  const float *beff;
+  void *out;            /* (T,H,W,C) fp16 */
+} GsnCabPassB;
+
+int gsn_cab_pass_b(const GsnCabPassB *d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHIFTNET_B200_H */

@@ -1,0 +1,71 @@
+// Shared device/host helpers for the shiftnet_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/shiftnet_b200.h"
+
+namespace gsn {
+
+// ---- host-side error plumbing -------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch();
+int check_launch(const char *what);   // cudaGetLastError -> GSN_E_CUDA + message
+
+#define GSN_REQUIRE(cond, ...)             \
+  do {                                     \
+    if (!(cond)) {                         \
+      gsn::set_error(__VA_ARGS__);         \
+      return GSN_E_BADARG;                 \
+    }                                      \
+  } while (0)
+
+// ---- small device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+  // 16-byte async copy; src-size 0 => zero fill (used for image borders / out-of-range frames)
+  uint32_t d = smem_u32(smem_dst);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<__half2 *>(&v));
+}
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8]) {
+  float2 a = unpack_half2(v.x), b = unpack_half2(v.y), c = unpack_half2(v.z), d = unpack_half2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]);
+  v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+}  // namespace gsn

@@ -1,0 +1,202 @@
+// Dense convolution as an implicit GEMM on tensor cores (mma.sync m16n8k16, fp16 in / fp32 acc).
+//
+// Covers every groups==1 nn.Conv2d of the reference path (see include/shiftnet_b200.h for the list of
+// call sites).  NHWC fp16 activations; one CTA = 16x16 output pixels x all output channels; each of the
+// 8 warps owns two output rows (two 16-pixel M tiles) so that every B fragment is used twice.
+// The input tile (with halo, up to 3 channel-concatenated sources) is staged in shared memory with
+// 16-byte cp.async (zero fill outside the image == the conv's zero padding); A fragments come from it
+// via ldmatrix with a per-tap pixel offset, B fragments stream from a pre-packed global buffer that
+// stays L1/L2 resident.
+//
+// HBM-bound by design for the narrow full-resolution layers (16->16 ch: 72 FLOP/B).
+#include "common.cuh"
+
+namespace gsn {
+
+template <int NT>
+__global__ void __launch_bounds__(256) conv_mma_kernel(const GsnConvDesc d, int IH, int IW, int pitch) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __half *tile = reinterpret_cast<__half *>(smem);
+  float *red = reinterpret_cast<float *>(smem + (size_t)IH * IW * pitch * 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.z;
+  const int ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16;
+  const int ix0 = ox0 * d.stride - d.pad, iy0 = oy0 * d.stride - d.pad;
+
+  // ---- stage the input tile ---------------------------------------------------------------------
+  {
+    const int chunks = d.cin_p >> 3;
+    const int total = IH * IW * chunks;
+    const int c1 = d.src_c[0], c2 = d.src_c[0] + d.src_c[1];
+    for (int i = tid; i < total; i += 256) {
+      const int ch = i % chunks, px = i / chunks;
+      const int ly = px / IW, lx = px - ly * IW;
+      const int gy = iy0 + ly, gx = ix0 + lx;
+      const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
+      const int c = ch * 8;
+      int s = 0, cb = 0;
+      if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
+      else if (c >= c1 && d.n_src > 1) { s = 1; cb = c1; }
+      const __half *base = reinterpret_cast<const __half *>(d.src[s]);
+      const __half *sp = valid ? base + (((size_t)t * d.Hin + gy) * d.Win + gx) * d.src_c[s] + (c - cb) : base;
+      cp_async16(tile + (size_t)px * pitch + c, sp, valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+
+  // ---- main loop --------------------------------------------------------------------------------
+  float acc[2][NT][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
+
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;  // output x within the M tile
+  const int akof = (lane >> 4) * 8;                     // k half (0 / 8) this lane addresses
+  const int ksteps = d.cin_p >> 4;
+  const uint2 *wp = reinterpret_cast<const uint2 *>(d.wpack);
+  const uint32_t tile_s = smem_u32(tile);
+  const int taps = d.ks * d.ks;
+
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ky = tap / d.ks, kx = tap - ky * d.ks;
+    const int ix = arow * d.stride + kx;
+    for (int k = 0; k < ksteps; ++k) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int iy = (2 * warp + m) * d.stride + ky;
+        const uint32_t addr = tile_s + (uint32_t)(((iy * IW + ix) * pitch + k * 16 + akof) * 2);
+        ldmatrix_x4(a[m][0], a[m][1], a[m][2], a[m][3], addr);
+      }
+      const uint2 *wk = wp + ((size_t)(tap * ksteps + k) * NT) * 32 + lane;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const uint2 b = __ldg(wk + n * 32);
+        mma16816(acc[0][n], a[0], b.x, b.y);
+        mma16816(acc[1][n], a[1], b.x, b.y);
+      }
+    }
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------------
+  const int g = lane >> 2, tig = lane & 3;
+  float csum[NT][2];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) csum[n][0] = csum[n][1] = 0.f;
+
+  __half *dst = reinterpret_cast<__half *>(d.dst);
+  const __half *res = reinterpret_cast<const __half *>(d.residual);
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int oy = oy0 + 2 * warp + m;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int ox = ox0 + g + hrow * 8;
+      const bool ok = (oy < d.Hout) && (ox < d.Wout);
+      const size_t opix = ((size_t)t * d.Hout + oy) * d.Wout + ox;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int co = n * 8 + tig * 2;
+        float v0 = acc[m][n][hrow * 2 + 0], v1 = acc[m][n][hrow * 2 + 1];
+        if (d.bias) { v0 += __ldg(d.bias + co); v1 += __ldg(d.bias + co + 1); }
+        if (d.has_prelu) {
+          v0 = v0 > 0.f ? v0 : v0 * d.prelu_slope;
+          v1 = v1 > 0.f ? v1 : v1 * d.prelu_slope;
+        }
+        if (!ok) continue;
+        if (res) {
+          const float2 r = unpack_half2(*reinterpret_cast<const uint32_t *>(res + opix * d.cout_p + co));
+          v0 += r.x; v1 += r.y;
+        }
+        csum[n][0] += v0; csum[n][1] += v1;
+        if (!d.pixel_shuffle) {
+          *reinterpret_cast<uint32_t *>(dst + opix * d.cout_p + co) = pack_half2(v0, v1);
+        } else {
+          // F.pixel_shuffle(.,2): conv channel co = c*4 + i*2 + j -> dst[c, 2y+i, 2x+j]; co is even => j = 0 / 1
+          const int cd = d.cout_p >> 2, c = co >> 2, i = (co >> 1) & 1;
+          const size_t dp = (((size_t)t * 2 * d.Hout + 2 * oy + i) * (2 * d.Wout) + 2 * ox) * cd + c;
+          dst[dp] = __float2half_rn(v0);
+          dst[dp + cd] = __float2half_rn(v1);
+        }
+      }
+    }
+  }
+
+  if (d.chan_partial) {
+    // deterministic per-tile channel sums: lanes (same tig) -> warp -> CTA
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v = csum[n][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) red[warp * d.cout_p + n * 8 + tig * 2 + j] = v;
+      }
+    __syncthreads();
+    if (tid < d.cout_p) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * d.cout_p + tid];
+      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * d.cout_p + tid] = s;
+    }
+  }
+}
+
+template <int NT>
+static int launch_conv(const GsnConvDesc &d, cudaStream_t st) {
+  const int IH = 15 * d.stride + d.ks, IW = IH;
+  const int pitch = d.cin_p + 8;
+  const size_t smem = (size_t)IH * IW * pitch * 2 + 8 * d.cout_p * sizeof(float);
+  if (smem > 227 * 1024) { set_error("conv_mma: tile needs %zu B smem", smem); return GSN_E_UNSUPPORTED; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((d.Wout + 15) / 16, (d.Hout + 15) / 16, d.T);
+  conv_mma_kernel<NT><<<grid, 256, smem, st>>>(d, IH, IW, pitch);
+  count_launch();
+  return check_launch("conv_mma");
+}
+
+}  // namespace gsn
+
+extern "C" int gsn_conv_tiles(int Hout, int Wout) { return ((Hout + 15) / 16) * ((Wout + 15) / 16); }
+
+extern "C" int gsn_conv_mma(const GsnConvDesc *dp, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(dp != nullptr, "conv_mma: null descriptor");
+  const GsnConvDesc &d = *dp;
+  GSN_REQUIRE(d.n_src >= 1 && d.n_src <= 3, "conv_mma: n_src=%d", d.n_src);
+  int csum = 0;
+  for (int i = 0; i < d.n_src; ++i) {
+    GSN_REQUIRE(d.src[i] && d.src_c[i] > 0 && d.src_c[i] % 8 == 0, "conv_mma: bad source %d (c=%d)", i, d.src_c[i]);
+    csum += d.src_c[i];
+  }
+  GSN_REQUIRE(csum == d.cin_p && d.cin_p % 16 == 0, "conv_mma: cin_p=%d must be the sum of sources (%d) and %%16", d.cin_p, csum);
+  GSN_REQUIRE(d.ks >= 1 && d.ks <= 3 && d.stride >= 1 && d.stride <= 2, "conv_mma: ks=%d stride=%d unsupported", d.ks, d.stride);
+  GSN_REQUIRE(d.T > 0 && d.Hin > 0 && d.Win > 0 && d.Hout > 0 && d.Wout > 0, "conv_mma: empty shape");
+  GSN_REQUIRE((d.Hin + 2 * d.pad - d.ks) / d.stride + 1 == d.Hout && (d.Win + 2 * d.pad - d.ks) / d.stride + 1 == d.Wout,
+              "conv_mma: output size %dx%d inconsistent with input %dx%d k%d s%d p%d", d.Hout, d.Wout, d.Hin, d.Win, d.ks,
+              d.stride, d.pad);
+  GSN_REQUIRE(d.wpack && d.dst, "conv_mma: null weights/dst");
+  GSN_REQUIRE(!d.pixel_shuffle || (d.cout_p % 4 == 0 && !d.residual && !d.chan_partial), "conv_mma: bad pixel_shuffle combination");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (d.cout_p) {
+    case 16: return launch_conv<2>(d, st);
+    case 32: return launch_conv<4>(d, st);
+    case 48: return launch_conv<6>(d, st);
+    case 64: return launch_conv<8>(d, st);
+    case 80: return launch_conv<10>(d, st);
+    default: set_error("conv_mma: cout_p=%d unsupported (16/32/48/64/80)", d.cout_p); return GSN_E_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,276 @@
+"""Forward orchestration of GShiftNet on the sm_100a kernels (csrc/), one ctypes call per kernel.
+
+Mirrors the reference control flow (gshift_deblur2.py:587-613,682-695,731-756) but every tensor op is one of
+our CUDA kernels; torch only provides device buffers and the current stream.  Activations are NHWC fp16 with
+channels padded to a multiple of 16.  No CPU path: constructing an Engine requires CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from . import packing as P
+
+_PAIRS = ["encoder_level1"] + [f"encoder_level1_{i}" for i in range(1, 8)]
+
+
+class Engine:
+    def __init__(self, spec, state_dict, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("shiftnet_b200: the engine runs on CUDA only (no CPU fallback)")
+        if spec.plus or spec.denoise:
+            raise NotImplementedError(
+                f"shiftnet_b200: arch {spec.name} is not implemented in the CUDA path yet (Ours+: C=80 / grouped RepConv; "
+                "denoise: the extra mid-block CALayer2 needs a third pass) -- only gshift_deblur2 runs so far")
+        self.spec = spec
+        self.dev = torch.device(device)
+        self.lib = L.load()
+        self.sd = {k: v.detach().to(self.dev, torch.float32) for k, v in state_dict.items()}
+        self.cache = {}
+        self.boff = 1 if spec.denoise else 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _new(self, *shape, dtype=torch.float16):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def _slope(self, key):
+        v = self.cache.get(("slope", key))
+        if v is None:
+            v = float(self.sd[key].item())
+            self.cache[("slope", key)] = v
+        return v
+
+    # ------------------------------------------------------------------ dense conv (tensor cores)
+    def conv(self, key, srcs, src_real, cout, stride=1, pad=None, prelu_key=None, residual=None, pixel_shuffle=False,
+             want_sums=False):
+        """srcs: list of NHWC tensors (T,H,W,Cp); src_real: their real channel counts."""
+        w = self.sd[key + ".weight"]
+        ks = w.shape[-1]
+        if pad is None:
+            pad = ks // 2
+        T, Hin, Win = srcs[0].shape[:3]
+        Hout = (Hin + 2 * pad - ks) // stride + 1
+        Wout = (Win + 2 * pad - ks) // stride + 1
+        cout_p = P.pad16(cout)
+        src_pad = [s.shape[3] for s in srcs]
+        ck = ("conv", key)
+        if ck not in self.cache:
+            wp = P.pack_conv_mma(w, src_real, src_pad, cout_p)
+            b = self.sd.get(key + ".bias")
+            self.cache[ck] = (wp, P.pack_bias(b, cout_p) if b is not None else None)
+        wp, bias = self.cache[ck]
+        if pixel_shuffle:
+            dst = self._new(T, 2 * Hout, 2 * Wout, cout_p // 4)
+        else:
+            dst = self._new(T, Hout, Wout, cout_p)
+        partial = None
+        if want_sums:
+            partial = self._new(T, self.lib.gsn_conv_tiles(Hout, Wout), cout_p, dtype=torch.float32)
+        d = L.ConvDesc()
+        d.T, d.Hin, d.Win, d.Hout, d.Wout = T, Hin, Win, Hout, Wout
+        d.n_src = len(srcs)
+        for i, s in enumerate(srcs):
+            assert s.is_contiguous() and s.dtype == torch.float16
+            d.src[i] = s.data_ptr()
+            d.src_c[i] = s.shape[3]
+        d.cin_p, d.cout_p, d.ks, d.stride, d.pad = sum(src_pad), cout_p, ks, stride, pad
+        d.wpack = wp.data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.has_prelu = 1 if prelu_key else 0
+        d.prelu_slope = self._slope(prelu_key) if prelu_key else 0.0
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.pixel_shuffle = 1 if pixel_shuffle else 0
+        d.chan_partial = partial.data_ptr() if partial is not None else None
+        d.dst = dst.data_ptr()
+        L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
+        return (dst, partial) if want_sums else dst
+
+    # ------------------------------------------------------------------ CAB (dense 3x3 + channel attention)
+    def cab(self, p, x, c, extra=None):
+        """gshift_deblur2.py:143-158.  ``extra`` is an optional tensor added to the result (stage shortcuts)."""
+        r1 = self.conv(p + ".body.0", [x], [c], c, prelu_key=p + ".body.1.weight")
+        r2, partial = self.conv(p + ".body.2", [r1], [c], c, want_sums=True)
+        ck = ("ca", p)
+        if ck not in self.cache:
+            self.cache[ck] = (self.sd[p + ".CA.conv_du.0.weight"].flatten(1).contiguous(),
+                              self.sd[p + ".CA.conv_du.2.weight"].flatten(1).contiguous())
+        w1, w2 = self.cache[ck]
+        T, H, W, cp = x.shape
+        s = self._new(T, cp, dtype=torch.float32)
+        L.check(self.lib.gsn_ca_scale(partial.data_ptr(), partial.shape[1], 1.0 / (H * W), w1.data_ptr(), w2.data_ptr(),
+                                      c, w1.shape[0], cp, T, s.data_ptr(), self._stream()), "ca_scale")
+        out = self._new(T, H, W, cp)
+        L.check(self.lib.gsn_scale_residual(x.data_ptr(), r2.data_ptr(), s.data_ptr(),
+                                            extra.data_ptr() if extra is not None else None, out.data_ptr(), T, H * W, cp,
+                                            self._stream()), "scale_residual")
+        return out
+
+    def seq_cabs(self, p, x, c):
+        i = 0
+        while f"{p}.{i}.body.0.weight" in self.sd:
+            x = self.cab(f"{p}.{i}", x, c)
+            i += 1
+        return x
+
+    def downsample(self, p, x, cin, cout):
+        if self.spec.denoise:
+            return self.conv(p + ".down.0", [x], [cin], cout, stride=2, pad=1, prelu_key=p + ".down.1.weight")
+        return self.conv(p + ".down", [x], [cin], cout, stride=2, pad=1)
+
+    def skip_upsample(self, p, x, cin, skip, cout):
+        """1x1 at low resolution, then bilinear x2 + skip (the two linear ops commute; gshift_deblur2.py:344-353)."""
+        y = self.conv(p + ".up.1", [x], [cin], cout)
+        T, h, w, cp = y.shape
+        out = self._new(T, 2 * h, 2 * w, cp)
+        L.check(self.lib.gsn_upsample2x_add(y.data_ptr(), skip.data_ptr(), out.data_ptr(), T, h, w, cp, self._stream()),
+                "upsample2x_add")
+        return out
+
+    def add(self, a, b):
+        out = torch.empty_like(a)
+        L.check(self.lib.gsn_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), self._stream()), "add")
+        return out
+
+    def tfr_unet(self, p, x):
+        """gshift_deblur2.py:682-695."""
+        n0, st = self.spec.n0, self.spec.unet_step
+        c1, c2, c3 = n0, n0 + st, n0 + 2 * st
+        enc1 = self.seq_cabs(p + ".encoder_level1", x, c1)
+        enc2 = self.seq_cabs(p + ".encoder_level2", self.downsample(p + ".down12", enc1, c1, c2), c2)
+        enc3 = self.seq_cabs(p + ".encoder_level3", self.downsample(p + ".down23", enc2, c2, c3), c3)
+        dec3 = self.seq_cabs(p + ".decoder_level3", enc3, c3)
+        y = self.skip_upsample(p + ".up32", dec3, c3, self.cab(p + ".skip_attn2", enc2, c2), c2)
+        dec2 = self.seq_cabs(p + ".decoder_level2", y, c2)
+        y = self.skip_upsample(p + ".up21", dec2, c2, self.cab(p + ".skip_attn1", enc1, c1), c1)
+        return self.seq_cabs(p + ".decoder_level1", y, c1)
+
+    # ------------------------------------------------------------------ fused shift + NAF block
+    def gated_cab(self, p, x, mode, debug_stage=0):
+        """One CAB2 (mode fwd/rev: shift folded into the load) or CAB1 step: pass A -> fold -> pass B."""
+        T, H, W, Cc = x.shape
+        shift = mode != L.MODE_CAB1
+        ck = ("gcab", p)
+        if ck not in self.cache:
+            self.cache[ck] = (P.pack_cab_pass_a(self.sd, p, Cc, shift, self.boff), P.pack_cab_fold(self.sd, p, self.boff))
+        blob, fw = self.cache[ck]
+        ntiles = self.lib.gsn_cab_tiles(mode, H, W)
+        z = self._new(T, H, W, Cc)
+        partial = self._new(T, ntiles, Cc, dtype=torch.float32)
+        a = L.CabPassA()
+        a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
+        a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), partial.data_ptr()
+        dbg = None
+        if debug_stage:
+            dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
+            a.debug_stage, a.debug_out = debug_stage, dbg.data_ptr()
+        L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
+        weff = self._new(T, Cc * Cc)
+        beff = self._new(T, Cc, dtype=torch.float32)
+        L.check(self.lib.gsn_cab_fold(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["du0"].data_ptr(), fw["du2"].data_ptr(),
+                                      fw["du0"].shape[0], fw["w3"].data_ptr(), fw["beta"].data_ptr(),
+                                      fw["bias3"].data_ptr() if fw["bias3"] is not None else None, Cc, T, weff.data_ptr(),
+                                      beff.data_ptr(), self._stream()), "cab_fold")
+        out = self._new(T, H, W, Cc)
+        b = L.CabPassB()
+        b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, a.circular
+        b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
+        L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
+        if debug_stage:
+            return out, z, dbg
+        return out
+
+    def shift_block(self, p, x):
+        """Encoder_shift_block.forward (gshift_deblur2.py:521-530): alternating fwd/rev (shift, CAB2, CAB1) pairs."""
+        for i in range(self.spec.pairs):
+            q = f"{p}.{_PAIRS[i]}"
+            x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if (i & 1) else L.MODE_CAB2_FWD)
+            x = self.gated_cab(q + ".1", x, L.MODE_CAB1)
+        return x
+
+    # ------------------------------------------------------------------ stage 1 (Encoder2, Ours-s topology)
+    def stage1(self, p, x):
+        """gshift_deblur2.py:587-613 / gshift_denoise2.py:583-609."""
+        sp = self.spec
+        n0, c = sp.n0, sp.c1
+        x = self.cab(p + ".concat", x, n0)
+        shortcut = x
+        y = self.conv(p + ".down01.0", [x], [n0], c, stride=2, pad=0, prelu_key=p + ".down01.1.weight")
+        for n in ("encoder_level1", "encoder_level1_1", "encoder_level1_2"):
+            y = self.shift_block(f"{p}.{n}", y)
+        enc11 = y
+        y = self.downsample(p + ".down12", enc11, c, c)
+        for n in ("encoder_level2", "encoder_level2_1", "encoder_level2_2",
+                  "decoder_level2", "decoder_level2_1", "decoder_level2_2"):
+            y = self.shift_block(f"{p}.{n}", y)
+        y = self.skip_upsample(p + ".up21", y, c, self.cab(p + ".skip_attn1", enc11, c), c)
+        for n in ("decoder_level1", "decoder_level1_1", "decoder_level1_2"):
+            y = self.shift_block(f"{p}.{n}", y)
+        sk = self.cab(p + ".skip_conv", shortcut, n0)
+        if sp.denoise:
+            up = self.conv(p + ".upsample0.upsample_conv", [y], [c], 4 * n0, pixel_shuffle=True)
+            out = self.conv(p + ".conv_hr0", [up, sk], [n0, n0], n0)                      # gshift_denoise2.py:607
+        else:
+            up = self.conv(p + ".upsample0.upsample_conv", [y], [c], 4 * n0, pixel_shuffle=True, prelu_key=p + ".act.weight")
+            out = self.conv(p + ".conv_hr0", [up], [n0], n0, residual=sk)                 # gshift_deblur2.py:611
+        return self.cab(p + ".out_conv", out, n0)
+
+    # ------------------------------------------------------------------ whole net
+    def forward(self, x, noise_map=None, past=2, future=2):
+        """GShiftNet.forward (gshift_deblur2.py:748-756, gshift_denoise2.py:744-753)."""
+        sp = self.spec
+        if x.dim() != 5 or x.shape[0] != 1:
+            raise ValueError(f"expected input (1,T,3,H,W), got {tuple(x.shape)}")
+        if x.dtype not in (torch.float16, torch.float32):
+            raise TypeError(f"unsupported input dtype {x.dtype}")
+        xin = x[0]
+        if sp.denoise:
+            if noise_map is None:
+                raise ValueError("denoise arch needs noise_map (1,T,1,H,W)")
+            xin = torch.cat((xin, noise_map[0].to(xin.dtype).expand(-1, 1, -1, -1)), dim=1)
+        xin = xin.contiguous()
+        T, cin, H, W = xin.shape
+        if H % 4 or W % 4:
+            raise ValueError(f"H and W must be multiples of 4 (got {H}x{W}); the reference scripts crop to %4")
+        if T - past - future <= 0:
+            raise ValueError("clip too short for the requested past/future context")
+        dt = L.DTYPE_F16 if xin.dtype == torch.float16 else L.DTYPE_F32
+        n0 = sp.n0
+        n0p = P.pad16(n0)
+        if "in" not in self.cache:
+            self.cache["in"] = P.pack_conv_in(self.sd["feat_extract.0.weight"], self.sd["feat_extract.0.bias"], n0p)
+            self.cache["out"] = P.pack_conv_out(self.sd["conv_last.weight"], n0p)
+        wi, bi = self.cache["in"]
+        f0 = self._new(T, H, W, n0p)
+        L.check(self.lib.gsn_conv_in(xin.data_ptr(), dt, T, cin, H, W, wi.data_ptr(), bi.data_ptr(), n0p, f0.data_ptr(),
+                                     self._stream()), "conv_in")
+        x0 = self.cab("feat_extract.1", f0, n0)
+        # stage 0 (gshift_deblur2.py:731-737)
+        f = x0
+        for i in range(1, sp.n_orb + 1):
+            f = self.tfr_unet(f"orb{i}", f)
+        if not sp.denoise:
+            f = self.add(f, x0)
+        sam0 = f
+        sam = self.conv("conv_trans", [f], [n0], n0)
+        dec = self.stage1("stage1", sam)
+        # stage 2 on the centre frames only (gshift_deblur2.py:738-746,755)
+        s = slice(past, T - future)
+        third = sam[s] if sp.denoise else sam0[s]
+        y = self.conv("rconcat", [x0[s], third, dec[s]], [n0, n0, n0], n0,
+                      prelu_key="lrelu.weight" if sp.denoise else None)
+        r = y
+        for i in range(1, sp.n_orb + 1):
+            r = self.tfr_unet(f"rorb{i}", r)
+        if not sp.denoise:
+            r = self.add(r, y)
+        To = T - past - future
+        out = torch.empty(To, 3, H, W, dtype=xin.dtype, device=self.dev)
+        wo = self.cache["out"]
+        L.check(self.lib.gsn_conv_out(r.data_ptr(), n0p, self.sd["conv_last.weight"].shape[-1], wo.data_ptr(),
+                                      xin[past:].data_ptr(), cin, dt, To, H, W, out.data_ptr(), self._stream()), "conv_out")
+        return out

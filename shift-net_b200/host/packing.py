@@ -1,0 +1,105 @@
+"""One-time weight re-packing: reference state_dict tensors (NCHW conv weights, fp32/fp16) -> the device
+layouts the kernels in csrc/ read.  Runs once per (net, device); layouts are documented next to the
+kernel that consumes them.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def pack_conv_mma(w: torch.Tensor, src_real, src_pad, cout_p: int) -> torch.Tensor:
+    """Dense conv weight (cout, sum(src_real), k, k) -> fp16 [tap][cin_p/16][cout_p/8][32 lanes][4]
+    (mma.m16n8k16 B fragments; csrc/conv_mma.cu).  Each source's real channels are placed at the start of
+    its padded slot, padding rows/cols are zero."""
+    w = w.float()
+    cout, cin, k, _ = w.shape
+    assert cin == sum(src_real)
+    cin_p = sum(src_pad)
+    assert cin_p % 16 == 0 and cout_p % 8 == 0 and cout <= cout_p
+    wp = torch.zeros(cout_p, cin_p, k * k, device=w.device)
+    ro = po = 0
+    for r, p in zip(src_real, src_pad):
+        wp[:cout, po:po + r] = w[:, ro:ro + r].reshape(cout, r, k * k)
+        ro += r
+        po += p
+    nt, ks = cout_p // 8, cin_p // 16
+    # n = nt*8 + g ; kk = kstep*16 + hi*8 + tig*2 + e ; lane = g*4 + tig ; regs (b0: hi=0, b1: hi=1) x e
+    v = wp.view(nt, 8, ks, 2, 4, 2, k * k)            # (nt, g, kstep, hi, tig, e, tap)
+    v = v.permute(6, 2, 0, 1, 4, 3, 5).contiguous()   # (tap, kstep, nt, g, tig, hi, e)
+    return v.reshape(-1).half()
+
+
+def pack_conv_in(w, b, cout_p):
+    """(cout, cin, 3, 3) -> fp32 [9][cin][cout_p], bias [cout_p] (csrc/io_convs.cu conv_in)."""
+    cout, cin = w.shape[:2]
+    wp = torch.zeros(9, cin, cout_p, device=w.device)
+    wp[:, :, :cout] = w.float().permute(2, 3, 1, 0).reshape(9, cin, cout)
+    bp = torch.zeros(cout_p, device=w.device)
+    if b is not None:
+        bp[:cout] = b.float()
+    return wp.contiguous(), bp
+
+
+def pack_conv_out(w, cp):
+    """(3, cin, k, k) -> fp32 [k*k][cp][3] (csrc/io_convs.cu conv_out)."""
+    cout, cin, k, _ = w.shape
+    wp = torch.zeros(k * k, cp, 3, device=w.device)
+    wp[:, :cin] = w.float().permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+    return wp.contiguous()
+
+
+def pack_bias(b, cout_p):
+    bp = torch.zeros(cout_p, device=b.device)
+    bp[:b.numel()] = b.float()
+    return bp
+
+
+def planar_chunks(w2d: torch.Tensor) -> torch.Tensor:
+    """(N, K) -> fp16 [K/8][N][8]: the k-chunk planar operand layout of csrc/shift_cab.cu."""
+    n, k = w2d.shape
+    return w2d.float().view(n, k // 8, 8).permute(1, 0, 2).contiguous().half()
+
+
+def pack_cab_pass_a(sd, p, C, shift, body_off=0):
+    """Pass-A weight blob of one CAB1/CAB2 (byte layout = PassACfg::OFF_* in csrc/shift_cab.cu).
+
+    body indices (gshift_deblur2.py:193-204): 0 1x1 | 1 RepConv2 | 3 RepConv | 4 1x1 ; ``body_off`` = 1 for the
+    denoise variants (extra CALayer2 at index 3)."""
+    k = body_off
+    parts = []
+    ln = torch.cat((sd[p + ".norm.weight"].float(), sd[p + ".norm.bias"].float()))
+    parts.append(ln.contiguous().view(torch.uint8))
+    if shift:
+        c1 = sd[p + ".conv1.weight"].float().view(C // 2, 9).t().contiguous().half()      # [9][C/2]
+        parts.append(c1.view(torch.uint8).reshape(-1))
+    w1 = sd[p + ".body.0.weight"].float().flatten(1)                                       # (2C, CIN)
+    parts.append(planar_chunks(w1).view(torch.uint8).reshape(-1))
+    da = sd[p + ".body.1.conv_2.weight"].float().view(2 * C, 9).t().contiguous().half()   # [9][2C]
+    parts.append(da.view(torch.uint8).reshape(-1))
+    w5 = sd[p + f".body.{3 + k}.conv_1.weight"].float().clone()                            # (C,1,5,5)
+    w3 = sd[p + f".body.{3 + k}.conv_2.weight"].float()
+    assert w5.shape[1] == 1, "grouped RepConv (Ours+) is not supported by this kernel yet"
+    w5[:, :, 1:4, 1:4] += w3
+    db = w5.view(C, 25).t().contiguous().half()                                            # [25][C]
+    parts.append(db.view(torch.uint8).reshape(-1))
+    w2 = sd[p + f".body.{4 + k}.weight"].float().flatten(1)                                # (2C, C)
+    parts.append(planar_chunks(w2).view(torch.uint8).reshape(-1))
+    return torch.cat([x.reshape(-1) for x in parts]).contiguous()
+
+
+def pack_cab_fold(sd, p, body_off=0):
+    k = body_off
+    ca = p + f".body.{6 + k}.conv_du"
+    last = p + f".body.{7 + k}"
+    d = dict(
+        du0=sd[ca + ".0.weight"].float().flatten(1).contiguous(),
+        du2=sd[ca + ".2.weight"].float().flatten(1).contiguous(),
+        w3=sd[last + ".weight"].float().flatten(1).contiguous(),
+        beta=sd[p + ".beta"].float().reshape(-1).contiguous(),
+        bias3=sd[last + ".bias"].float().contiguous() if (last + ".bias") in sd else None,
+    )
+    return d

@@ -1,0 +1,143 @@
+"""CPU suite: the oracle against the committed reference goldens, the host logic, and the C-ABI exports."""
+import ctypes
+import hashlib
+import importlib
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+
+sys.path.insert(0, os.path.join(gio.ROOT, "oracle"))
+import shiftnet_oracle as O  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize("arch", gio.ARCH_NAMES)
+def test_state_dict_keys_match_reference(arch):
+    sd, _ = gio.synthetic_checkpoint(arch)
+    ref = gio.load_keys(arch)
+    assert {k: list(v.shape) for k, v in sd.items()} == ref
+
+
+@pytest.mark.parametrize("arch", gio.ARCH_NAMES)
+def test_shift_index_map_bit_exact(arch):
+    """channel_shift fwd/rev is pure data movement: sha256 of the fp32 bytes must equal the reference's."""
+    _, spec = gio.synthetic_checkpoint(arch)
+    g = gio.load_golden(arch)
+    x = gio.module_input("shift", spec)
+    for name, rev in (("shift_fwd", False), ("shift_rev", True)):
+        y = O.channel_shift(x, rev, O.ARCHS[arch].circular).contiguous().numpy().astype(np.float32)
+        assert list(y.shape) == list(g[name + "_shape"])
+        assert hashlib.sha256(y.tobytes()).digest() == bytes(g[name + "_sha256"])
+
+
+@pytest.mark.parametrize("arch", gio.ARCH_NAMES)
+def test_oracle_modules_match_reference(arch):
+    sd, spec = gio.synthetic_checkpoint(arch)
+    osp = O.ARCHS[arch]
+    g = gio.load_golden(arch)
+    xs = gio.module_input("shift", spec)
+    blk = "stage1.decoder_level1"
+    c = spec.c1
+    got = {
+        "cab2_fwd": O.cab2(sd, blk + ".encoder_level1.0", O.channel_shift(xs, False, osp.circular), c, osp.denoise),
+        "cab2_rev": O.cab2(sd, blk + ".encoder_level1_1.0", O.channel_shift(xs, True, osp.circular), c, osp.denoise),
+        "cab1": O.cab1(sd, blk + ".encoder_level1.1", xs, osp.denoise),
+        "block": O.shift_block(sd, blk, xs, osp),
+        "cab": O.cab(sd, "feat_extract.1", gio.module_input("cab", spec)),
+        "tfr": O.tfr_unet(sd, "orb1", gio.module_input("tfr", spec), osp),
+        "stage1": O.stage1(sd, "stage1", gio.module_input("stage1", spec), osp),
+    }
+    for k, v in got.items():
+        ref = torch.from_numpy(g[k])
+        assert v.shape == ref.shape, k
+        # same torch build => bit-exact here; allow a few ulp for other CPUs / oneDNN paths
+        assert torch.allclose(v, ref, rtol=1e-4, atol=1e-5), (k, (v - ref).abs().max().item())
+
+
+@pytest.mark.parametrize("arch", gio.ARCH_NAMES)
+def test_oracle_full_forward_matches_reference(arch):
+    sd, spec = gio.synthetic_checkpoint(arch)
+    g = gio.load_golden(arch)
+    x, nm = gio.clip_input(spec)
+    out = O.gshiftnet_forward(sd, O.ARCHS[arch], x, nm)
+    ref = torch.from_numpy(g["full"])
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5), (out - ref).abs().max().item()
+
+
+def test_shift_offsets_table():
+    for c, n_single_outer, n_inner in ((64, 1, 2), (80, 2, 1)):
+        offs = O.shift_offsets(c)
+        assert len(offs) == c // 2
+        assert offs[0] == (8, 8) and offs[-1] == (-4, -4)
+        assert all(abs(dy) in (0, 4, 8) and abs(dx) in (0, 4, 8) and (dy, dx) != (0, 0) for dy, dx in offs)
+        assert len(set(offs)) == 24
+
+
+def test_roll_clamped_vs_circular_edge_frames():
+    x = torch.arange(3 * 4 * 2 * 2, dtype=torch.float32).view(3, 4, 2, 2)
+    yc, _ = O.temporal_roll(x, False, True)
+    yn, _ = O.temporal_roll(x, False, False)
+    assert torch.equal(yc[0, :2], x[2, 2:]) and torch.equal(yn[0], x[0])      # wrap vs un-swapped frame 0
+    assert torch.equal(yc[1:], yn[1:])
+    yc, _ = O.temporal_roll(x, True, True)
+    yn, _ = O.temporal_roll(x, True, False)
+    assert torch.equal(yc[2, 2:], x[0, :2]) and torch.equal(yn[2], x[2])
+    assert torch.equal(yc[:2], yn[:2])
+
+
+def test_cabi_exports_every_declared_symbol():
+    lib_mod = importlib.import_module("shift-net_b200.host.lib")
+    header = open(os.path.join(gio.ROOT, "include", "shiftnet_b200.h")).read()
+    declared = set(re.findall(r"\b(gsn_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(lib_mod.EXPORTS), declared ^ set(lib_mod.EXPORTS)
+    if not os.path.exists(lib_mod.LIB_PATH):
+        pytest.skip("library not built (run __graft_entry__.build())")
+    handle = ctypes.CDLL(lib_mod.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.gsn_version() >= 100
+
+
+def test_product_path_never_imports_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(gio.ROOT, "shift-net_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                if "oracle" in open(os.path.join(d, f), errors="ignore").read().replace("no oracle", ""):
+                    bad.append(f)
+    for d, _, files in os.walk(os.path.join(gio.ROOT, "basicsr")):
+        for f in files:
+            if f.endswith(".py") and "oracle" in open(os.path.join(d, f)).read():
+                bad.append(f)
+    assert not bad, bad
+
+
+def test_cpu_input_fails_loudly():
+    from basicsr.models.archs.gshift_deblur2 import GShiftNet
+    net = GShiftNet(future_frames=2, past_frames=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 6, 3, 16, 16))
+
+
+def test_weight_packing_layouts():
+    P = gio.pkg("host.packing")
+    w = torch.randn(14, 28, 3, 3)
+    wp = P.pack_conv_mma(w, [14, 14], [16, 16], 16).view(9, 2, 2, 32, 4).float()
+    # lane l (g=l>>2, tig=l&3) of n-tile nt, k-step ks holds W[nt*8+g][ks*16 + {2tig, 2tig+1, 2tig+8, 2tig+9}]
+    for tap, ks, nt, lane in ((0, 0, 0, 0), (4, 1, 1, 13), (8, 0, 1, 31)):
+        g_, tig = lane >> 2, lane & 3
+        n = nt * 8 + g_
+        for j, kk in enumerate((2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9)):
+            kp = ks * 16 + kk           # padded input channel -> (source, real channel)
+            src, c = divmod(kp, 16)
+            exp = w[n, src * 14 + c, tap // 3, tap % 3].half().float() if (n < 14 and c < 14) else torch.tensor(0.0)
+            assert wp[tap, ks, nt, lane, j] == exp
+    pc = P.planar_chunks(torch.arange(16 * 24, dtype=torch.float32).view(16, 24))
+    assert pc.shape == (3, 16, 8) and pc[2, 5, 3] == 5 * 24 + 2 * 8 + 3
