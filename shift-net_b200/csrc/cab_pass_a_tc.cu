@@ -1,0 +1,614 @@
+// Pass A of the fused shift + NAF block, Blackwell-native version (sm_100a):
+//   * both 1x1 channel-mixing convs are tcgen05.mma (M=128 pixel tiles, N=2C, K-major no-swizzle operands in the
+//     k-chunk planar shared-memory layout, fp32 accumulators in TMEM, issued by one thread, completion on an mbarrier);
+//   * TMEM doubles as the parking space of the 2C-wide tensor (4 x 128 columns = all 512 columns for the 22x22 halo'd
+//     region), which is what lets a 16x16-pixel tile with its 3-pixel halo fit next to the gather bounding box;
+//   * depthwise 3x3 / 5x5 stages run on CUDA cores with packed HFMA2 in "scatter" form: a thread walks down a column,
+//     each loaded input row updates the 3 (5) output rows it contributes to, weights live in registers;
+//   * the grouped spatial-temporal shift is a per-channel index-offset gather out of a staged bounding box of the
+//     neighbour frame's half of the channels, fused with conv1 (dw3x3) and the LayerNorm in the load stage.
+//
+// Reference semantics: gshift_deblur2.py:186-258 (CAB1/CAB2), :465-519 (spatial_shift2 / channel_shift).
+// Stage order and zero-padding rules are identical to the mma.sync version in shift_cab.cu (kept as a cross-check).
+#include "common.cuh"
+#include "shift_common.cuh"
+
+namespace gsn {
+
+constexpr int kTcThreads = 512;
+
+// ---- tcgen05 / mbarrier wrappers ------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// element (row r, k) lives at start + (r%8)*16 + (r/8)*SBO + (k%8)*2 + (k/8)*LBO   [bytes]
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// ---- packed half helpers --------------------------------------------------------------------------
+struct H8 {
+  __half2 h[4];
+};
+__device__ __forceinline__ H8 lds_h8(const unsigned char *p) {
+  const uint4 v = *reinterpret_cast<const uint4 *>(p);
+  H8 r;
+  r.h[0] = *reinterpret_cast<const __half2 *>(&v.x);
+  r.h[1] = *reinterpret_cast<const __half2 *>(&v.y);
+  r.h[2] = *reinterpret_cast<const __half2 *>(&v.z);
+  r.h[3] = *reinterpret_cast<const __half2 *>(&v.w);
+  return r;
+}
+__device__ __forceinline__ void sts_h8(unsigned char *p, const H8 &a) {
+  uint4 v;
+  v.x = *reinterpret_cast<const uint32_t *>(&a.h[0]);
+  v.y = *reinterpret_cast<const uint32_t *>(&a.h[1]);
+  v.z = *reinterpret_cast<const uint32_t *>(&a.h[2]);
+  v.w = *reinterpret_cast<const uint32_t *>(&a.h[3]);
+  *reinterpret_cast<uint4 *>(p) = v;
+}
+__device__ __forceinline__ void h8_fma(H8 &acc, const H8 &a, const H8 &w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc.h[i] = __hfma2(a.h[i], w.h[i], acc.h[i]);
+}
+__device__ __forceinline__ void h8_mul(H8 &acc, const H8 &a, const H8 &w) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc.h[i] = __hmul2(a.h[i], w.h[i]);
+}
+
+// ---- configuration ----------------------------------------------------------------------------------
+template <int C, bool SHIFT>
+struct TcCfg {
+  static constexpr int TW = 16, TH = 16;
+  static constexpr int HC = C / 2;
+  static constexpr int CIN = SHIFT ? C + HC : C;
+  static constexpr int KC1 = CIN / 8, KC2 = C / 8, NC = 2 * C / 8;  // k-chunks of GEMM1/GEMM2, chunks of the 2C tensor
+  static constexpr int R1W = TW + 6, R1H = TH + 6, M1 = R1W * R1H;   // 22x22 = 484: region of the 2C tensor
+  static constexpr int MT1 = (M1 + 127) / 128;                       // 4 UMMA M tiles
+  static constexpr int R2W = TW + 4, R2H = TH + 4, M2 = R2W * R2H;   // 20x20 gated region
+  static constexpr int M3 = TW * TH, MT3 = M3 / 128;                 // 256 output pixels, 2 UMMA M tiles
+  static constexpr int BW = TW + 24, BH = TH + 24;                   // 40x40 gather bounding box
+  static constexpr int N = 2 * C;                                    // UMMA N (128)
+  static_assert(MT1 * N <= 512, "GEMM1 accumulators must fit the 512 TMEM columns");
+  // weight blob offsets (identical to PassACfg in shift_cab.cu / host/packing.py)
+  static constexpr int OFF_LN = 0;
+  static constexpr int OFF_C1 = OFF_LN + 2 * CIN * 4;
+  static constexpr int OFF_W1 = OFF_C1 + (SHIFT ? 9 * HC * 2 : 0);
+  static constexpr int W1_BYTES = KC1 * N * 16;
+  static constexpr int OFF_DA = OFF_W1 + W1_BYTES;
+  static constexpr int DA_BYTES = 9 * 2 * C * 2;
+  static constexpr int OFF_DB = OFF_DA + DA_BYTES;
+  static constexpr int DB_BYTES = 25 * C * 2;
+  static constexpr int OFF_W2 = OFF_DB + DB_BYTES;
+  static constexpr int W2_BYTES = KC2 * N * 16;
+  static constexpr int BLOB = OFF_W2 + W2_BYTES;
+  static constexpr int WT2_BYTES = DA_BYTES + DB_BYTES + W2_BYTES;   // contiguous tail of the blob
+  // plane pitches
+  static constexpr int P1 = (M1 + 1) * 16, P2 = (M2 + 1) * 16, P3 = (M3 + 1) * 16;
+  // shared memory map.  Phase 1: [X | W1 | A1 | R12]; phase 2: [X | G1 ........ | GATED | WT2], A2/Z alias G1.
+  static constexpr int S_X = 0;                                      // LN params, conv1 weights, barrier, tmem ptr, sums
+  static constexpr int X_LN = 0, X_C1 = 1024, X_BAR = 1728, X_TMEM = 1744, X_RED = 1792, X_BYTES = 1792 + 2 * C * 4;
+  static constexpr int S_W1 = (X_BYTES + 127) / 128 * 128;
+  static constexpr int S_A1 = S_W1 + W1_BYTES;
+  static constexpr int A1_BYTES = KC1 * P1;
+  static constexpr int S_R = (S_A1 + A1_BYTES + 127) / 128 * 128;
+  static constexpr int R12_BYTES = SHIFT ? BW * BH * HC * 2 : 0;
+  static constexpr int S_G1 = S_W1;
+  static constexpr int G1_BYTES = NC * P1;
+  static constexpr int S_GT = ((S_G1 + G1_BYTES > S_R ? S_G1 + G1_BYTES : S_R) + 127) / 128 * 128;
+  static constexpr int GT_BYTES = KC2 * P2;
+  static constexpr int S_WT2 = (S_GT + GT_BYTES + 127) / 128 * 128;
+  static constexpr int END2 = S_WT2 + WT2_BYTES;
+  static constexpr int END1 = S_R + R12_BYTES;
+  static constexpr int SMEM = END1 > END2 ? END1 : END2;
+  static constexpr int S_A2 = S_G1;                                  // GEMM2 operand, then the z staging tile
+  static_assert(2 * CIN * 4 <= 1024 && 9 * HC * 2 <= 704, "X region layout");
+  static_assert(KC2 * P3 <= G1_BYTES, "A2 aliases G1");
+  static_assert(!SHIFT || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box, not over A1/W1");
+  static_assert(SHIFT || S_WT2 >= S_A1 + A1_BYTES, "WT2 must not overlap A1 while GEMM1 reads it");
+  static_assert(S_A1 + (KC1 - 1) * P1 + (MT1 * 128) * 16 <= SMEM, "UMMA rows beyond M1 must stay inside the allocation");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <int C, bool SHIFT>
+__global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnCabPassA d, const ShiftTable tab) {
+  using K = TcCfg<C, SHIFT>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.z, x0 = blockIdx.x * K::TW, y0 = blockIdx.y * K::TH;
+  const __half *xg = reinterpret_cast<const __half *>(d.x);
+  const unsigned char *wb = reinterpret_cast<const unsigned char *>(d.wblob);
+  const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
+  const size_t frame = (size_t)d.H * d.W * C;
+  const uint32_t bar = smem_u32(smem + K::S_X + K::X_BAR);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + K::S_X + K::X_TMEM);
+
+  // ---- P0: async loads (small params, W1, gather box), TMEM allocation, barrier init ---------------
+  {
+    for (int i = tid; i < (K::OFF_W1 - K::OFF_LN) / 16; i += kTcThreads) {  // LN params (+ conv1 weights)
+      const int off = i * 16;
+      unsigned char *dst = (off < K::OFF_C1) ? smem + K::S_X + K::X_LN + off : smem + K::S_X + K::X_C1 + (off - K::OFF_C1);
+      cp_async16(dst, wb + off, true);
+    }
+    for (int i = tid; i < K::W1_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
+    if (SHIFT) {
+      const bool fwd = d.mode == GSN_MODE_CAB2_FWD;
+      const __half *src = xg + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
+      constexpr int CH = K::HC / 8;
+      for (int i = tid; i < K::BW * K::BH * CH; i += kTcThreads) {
+        const int ch = i % CH, p = i / CH, by = p / K::BW, bx = p - by * K::BW;
+        const int gy = y0 - 12 + by, gx = x0 - 12 + bx;
+        const bool valid = gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
+        const __half *sp = valid ? src + ((size_t)gy * d.W + gx) * C + ch * 8 : src;
+        cp_async16(smem + K::S_R + (size_t)p * K::HC * 2 + ch * 16, sp, valid);
+      }
+    } else {
+      for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
+    }
+    cp_async_commit();
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    if (tid == 32) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- P1a (SHIFT): per-channel spatial-shift gather fused with conv1 (dw3x3, zero pad) -> raw A1 planes --------
+  if (SHIFT) {
+    const __half *wc1 = reinterpret_cast<const __half *>(smem + K::S_X + K::X_C1);
+    const __half *r12 = reinterpret_cast<const __half *>(smem + K::S_R);
+    constexpr int SEG = K::R1W / 2;  // 11-pixel row segments
+    for (int item = tid; item < K::HC * K::R1H * 2; item += kTcThreads) {
+      const int c = item % K::HC, rest = item / K::HC;
+      const int ry = rest % K::R1H, seg = rest / K::R1H;
+      const int dy = tab.dy[c], dx = tab.dx[c];
+      const int gy = y0 - 3 + ry;
+      float w[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) w[i] = __half2float(wc1[i * K::HC + c]);
+      bool rowok[3];
+      int rowoff[3];
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        const int sy = gy + ty - 1;                         // row in the shifted tensor: must be inside the image
+        rowok[ty] = sy >= 0 && sy < d.H;
+        rowoff[ty] = (ry + ty - 1 - dy + 9) * K::BW - dx + 9;  // + column gives the source pixel inside the box
+      }
+      const int rx0 = seg * SEG;
+      float v[3][3];
+      auto load_col = [&](int col, float(&o)[3]) {        // col = region column of the shifted tensor
+        const int sx = x0 - 3 + col;
+        const bool cok = sx >= 0 && sx < d.W;
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty)
+          o[ty] = (cok && rowok[ty]) ? __half2float(r12[(rowoff[ty] + col) * K::HC + c]) : 0.f;
+      };
+      {
+        float a[3], b[3];
+        load_col(rx0 - 1, a);
+        load_col(rx0, b);
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) { v[ty][0] = 0.f; v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+      }
+      unsigned char *dstp = smem + K::S_A1 + (C / 8 + c / 8) * K::P1 + (c & 7) * 2;
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) {
+        const int rx = rx0 + i;
+        float nc[3];
+        load_col(rx + 1, nc);
+        float acc = 0.f;
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) {
+          v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty];
+          acc = fmaf(v[ty][0], w[ty * 3 + 0], acc);
+          acc = fmaf(v[ty][1], w[ty * 3 + 1], acc);
+          acc = fmaf(v[ty][2], w[ty * 3 + 2], acc);
+        }
+        *reinterpret_cast<__half *>(dstp + (ry * K::R1W + rx) * 16) = __float2half_rn(acc);
+      }
+    }
+    __syncthreads();
+    // the gather box is dead now: stream the phase-2 weights (dw taps + W2) into its tail
+    for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
+    cp_async_commit();
+  }
+
+  // ---- P1b: LayerNorm over the CIN channels of every region pixel -> A1 (zero rows outside the image) ----
+  {
+    const float *ln_g = reinterpret_cast<const float *>(smem + K::S_X + K::X_LN);
+    const float *ln_b = ln_g + K::CIN;
+    constexpr int NV = SHIFT ? 24 : 16;
+    constexpr int ITEMS = (K::M1 + 7) / 8 * 8 * 4;   // whole warps only (quad shuffles below)
+    for (int item = tid; item < ITEMS; item += kTcThreads) {
+      const int q = item >> 2, j = item & 3;
+      const int ry = q / K::R1W, rx = q - ry * K::R1W;
+      const int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
+      const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
+      float v[NV];
+      int chunk_of[NV / 8];
+      if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
+      else { chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1; }
+      if (inimg) {
+        const size_t pix = ((size_t)gy * d.W + gx) * C;
+        if (SHIFT) {
+          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8)), *reinterpret_cast<float(*)[8]>(&v[0]));
+          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
+          unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A1 + (C / 8 + j) * K::P1 + q * 16), *reinterpret_cast<float(*)[8]>(&v[16]));
+        } else {
+          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16)), *reinterpret_cast<float(*)[8]>(&v[0]));
+          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += v[i];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const float mu = s * (1.f / K::CIN);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      const float rstd = rsqrtf(ss * (1.f / K::CIN) + 1e-6f);
+      if (q < K::M1) {
+#pragma unroll
+        for (int k = 0; k < NV / 8; ++k) {
+          float o[8];
+          const int cbase = chunk_of[k] * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = inimg ? (v[k * 8 + i] - mu) * rstd * ln_g[cbase + i] + ln_b[cbase + i] : 0.f;
+          *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
+        }
+      }
+    }
+    fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
+    __syncthreads();
+  }
+  if (d.debug_stage == 1) {
+    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
+               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC1 * K::M1;
+    for (int i = tid; i < K::KC1 * K::M1; i += kTcThreads)
+      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A1 + (i / K::M1) * K::P1 + (i % K::M1) * 16);
+  }
+
+  // ---- P2: GEMM1 on the tensor core: D[m-tile] (128 x 2C, TMEM) = A1 (128 x CIN) . W1^T ----------------------
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(128, K::N);
+    const uint32_t a_s = smem_u32(smem + K::S_A1), w_s = smem_u32(smem + K::S_W1);
+#pragma unroll 1
+    for (int m = 0; m < K::MT1; ++m) {
+#pragma unroll
+      for (int k = 0; k < K::KC1 / 2; ++k) {
+        const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P1 + m * 128 * 16, K::P1, 128);
+        const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
+        umma_f16(tmem + m * K::N, ad, bd, idesc, k > 0);
+      }
+    }
+    umma_commit(bar);
+  }
+  if (SHIFT) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather)
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
+
+  // ---- P3: TMEM -> fp16 G1 planes (all 2C channels of the region) ----------------------------------------------
+  {
+    const int quarter = warp & 3, sub = warp >> 2;   // a warp may only touch TMEM lanes [32*quarter, +32)
+    for (int u = sub; u < K::MT1 * (K::N / 32); u += kTcThreads / 128) {
+      const int m = u / (K::N / 32), cg = u % (K::N / 32);
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32, v);
+      const int px = m * 128 + quarter * 32 + lane;
+      if (px < K::M1) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint4 o;
+          o.x = pack_half2(__uint_as_float(v[c4 * 8 + 0]), __uint_as_float(v[c4 * 8 + 1]));
+          o.y = pack_half2(__uint_as_float(v[c4 * 8 + 2]), __uint_as_float(v[c4 * 8 + 3]));
+          o.z = pack_half2(__uint_as_float(v[c4 * 8 + 4]), __uint_as_float(v[c4 * 8 + 5]));
+          o.w = pack_half2(__uint_as_float(v[c4 * 8 + 6]), __uint_as_float(v[c4 * 8 + 7]));
+          *reinterpret_cast<uint4 *>(smem + K::S_G1 + (cg * 4 + c4) * K::P1 + px * 16) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- P4: dw3x3 + id on both halves, SimpleGate -> GATED (zero outside the image) ---------------------------------
+  {
+    constexpr int NSTRIP = 3, SROWS = (K::R2H + NSTRIP - 1) / NSTRIP;  // 7,7,6 output rows
+    const unsigned char *wda = smem + K::S_WT2;
+    for (int item = tid; item < K::KC2 * K::R2W * NSTRIP; item += kTcThreads) {
+      const int x = item % K::R2W, rest = item / K::R2W;
+      const int p = rest % K::KC2, strip = rest / K::KC2;
+      const int r0 = strip * SROWS, r1 = min(r0 + SROWS, K::R2H);
+      H8 res[SROWS];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int chunk = half * K::KC2 + p;
+        const unsigned char *pl = smem + K::S_G1 + chunk * K::P1;
+        H8 w[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] = lds_h8(wda + (i * 2 * C + chunk * 8) * 2);
+        H8 acc0, acc1, ctr_prev;
+#pragma unroll
+        for (int i = 0; i < SROWS + 2; ++i) {           // input region row r0 + i feeds output rows (r0+i-2 .. r0+i)
+          const int row = r0 + i;
+          if (row < r1 + 2) {
+            const unsigned char *rp = pl + (row * K::R1W + x) * 16;
+            const H8 v0 = lds_h8(rp), v1 = lds_h8(rp + 16), v2 = lds_h8(rp + 32);
+            if (i >= 2) {                               // output row r0+i-2 completes with kernel row 2
+              h8_fma(acc0, v0, w[6]); h8_fma(acc0, v1, w[7]); h8_fma(acc0, v2, w[8]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc0.h[q] = __hadd2(acc0.h[q], ctr_prev.h[q]);   // + identity (RepConv2)
+              if (half == 0) res[i - 2] = acc0;
+              else {
+                const int orow = row - 2;
+                const int gy = y0 - 2 + orow, gx = x0 - 2 + x;
+                H8 o;
+                if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) h8_mul(o, res[i - 2], acc0);
+                else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) o.h[q] = __float2half2_rn(0.f);
+                }
+                sts_h8(smem + K::S_GT + p * K::P2 + (orow * K::R2W + x) * 16, o);
+              }
+            }
+            if (i >= 1) {                               // output row r0+i-1: kernel row 1 (centre row)
+              acc0 = acc1;
+              h8_fma(acc0, v0, w[3]); h8_fma(acc0, v1, w[4]); h8_fma(acc0, v2, w[5]);
+              ctr_prev = v1;
+            }
+            h8_mul(acc1, v0, w[0]);                     // output row r0+i: kernel row 0 starts a new accumulator
+            h8_fma(acc1, v1, w[1]); h8_fma(acc1, v2, w[2]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (d.debug_stage == 2) {
+    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
+               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M2;
+    for (int i = tid; i < K::KC2 * K::M2; i += kTcThreads)
+      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_GT + (i / K::M2) * K::P2 + (i % K::M2) * 16);
+  }
+
+  // ---- P5: dw5x5 (+ merged dw3x3) + id on the gated tensor -> A2 (GEMM2 operand) -----------------------------------
+  {
+    constexpr int NSTRIP = 2, SROWS = K::TH / NSTRIP;   // 8 output rows per strip
+    const unsigned char *wdb = smem + K::S_WT2 + K::DA_BYTES;
+    for (int item = tid; item < 2 * K::KC2 * K::TW * NSTRIP; item += kTcThreads) {
+      // lanes = (half chunk parity, x): consecutive lanes read consecutive 8-byte words -> conflict-free LDS.64
+      const int e = item & 1, x = (item >> 1) % K::TW, rest = (item >> 1) / K::TW;
+      const int hc = (rest % K::KC2) * 2 + e, strip = rest / K::KC2;   // hc: 4-channel half chunk
+      const int r0 = strip * SROWS;
+      const unsigned char *pl = smem + K::S_GT + (hc >> 1) * K::P2 + (hc & 1) * 8;
+      __half2 w[25][2];
+#pragma unroll
+      for (int i = 0; i < 25; ++i) {
+        const uint2 ww = *reinterpret_cast<const uint2 *>(wdb + (i * C + hc * 4) * 2);
+        w[i][0] = *reinterpret_cast<const __half2 *>(&ww.x);
+        w[i][1] = *reinterpret_cast<const __half2 *>(&ww.y);
+      }
+      __half2 acc[5][2], ctr[3][2];
+#pragma unroll
+      for (int i = 0; i < SROWS + 4; ++i) {             // gated row r0 + i feeds output rows r0+i-4 .. r0+i
+        const unsigned char *rp = pl + ((r0 + i) * K::R2W + x) * 16;
+        __half2 v[5][2];
+#pragma unroll
+        for (int tx = 0; tx < 5; ++tx) {
+          const uint2 vv = *reinterpret_cast<const uint2 *>(rp + tx * 16);
+          v[tx][0] = *reinterpret_cast<const __half2 *>(&vv.x);
+          v[tx][1] = *reinterpret_cast<const __half2 *>(&vv.y);
+        }
+        // slot s = i % 5 holds the accumulator of output row (r0 + i) ; kernel row ky = i - (out row index)
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          const int oi = i - ky;                        // output row index within the strip
+          if (oi < 0 || oi >= SROWS) continue;
+          const int s = oi % 5;
+#pragma unroll
+          for (int tx = 0; tx < 5; ++tx)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              acc[s][e] = (ky == 0 && tx == 0) ? __hmul2(v[tx][e], w[ky * 5 + tx][e]) : __hfma2(v[tx][e], w[ky * 5 + tx][e], acc[s][e]);
+        }
+        // centre value of gated row r0+i is the identity term of output row oi = i - 2
+        ctr[i % 3][0] = v[2][0]; ctr[i % 3][1] = v[2][1];
+        const int od = i - 4;                           // output row completed by this input row
+        if (od >= 0) {
+          const int s = od % 5, cs = (od + 2) % 3;
+          uint2 o;
+          __half2 o0 = __hadd2(acc[s][0], ctr[cs][0]), o1 = __hadd2(acc[s][1], ctr[cs][1]);
+          o.x = *reinterpret_cast<uint32_t *>(&o0);
+          o.y = *reinterpret_cast<uint32_t *>(&o1);
+          *reinterpret_cast<uint2 *>(smem + K::S_A2 + (hc >> 1) * K::P3 + ((r0 + od) * K::TW + x) * 16 + (hc & 1) * 8) = o;
+        }
+      }
+    }
+    fence_async_proxy();
+    __syncthreads();
+  }
+  if (d.debug_stage == 3) {
+    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
+               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M3;
+    for (int i = tid; i < K::KC2 * K::M3; i += kTcThreads)
+      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A2 + (i / K::M3) * K::P3 + (i % K::M3) * 16);
+  }
+
+  // ---- P6: GEMM2 on the tensor core: (256 x C) . W2^T -> TMEM columns [0, 2*N) -------------------------------------
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(128, K::N);
+    const uint32_t a_s = smem_u32(smem + K::S_A2), w_s = smem_u32(smem + K::S_WT2 + K::DA_BYTES + K::DB_BYTES);
+#pragma unroll
+    for (int m = 0; m < K::MT3; ++m)
+#pragma unroll
+      for (int k = 0; k < K::KC2 / 2; ++k) {
+        const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P3 + m * 128 * 16, K::P3, 128);
+        const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
+        umma_f16(tmem + m * K::N, ad, bd, idesc, k > 0);
+      }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 1);
+  tc_fence_after();
+  __syncthreads();                 // A2 is dead: its space becomes the z staging tile
+
+  // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store + per-tile channel sums ---
+  {
+    const int quarter = warp & 3, sub = warp >> 2;
+    for (int u = sub; u < K::MT3 * (C / 32); u += kTcThreads / 128) {
+      const int m = u / (C / 32), cg = u % (C / 32);
+      uint32_t a[32], b[32];
+      const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32;
+      tmem_ld32(base, a);
+      tmem_ld32(base + C, b);
+      const int px = m * 128 + quarter * 32 + lane;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = __uint_as_float(a[c4 * 8 + i]) * sigmoidf_fast(__uint_as_float(b[c4 * 8 + i]));
+        *reinterpret_cast<uint4 *>(smem + K::S_A2 + (cg * 4 + c4) * K::P3 + px * 16) = pack8(z);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    __half *zg = reinterpret_cast<__half *>(d.z) + (size_t)t * frame;
+    for (int i = tid; i < K::M3 * K::KC2; i += kTcThreads) {
+      const int ch = i % K::KC2, p = i / K::KC2;
+      const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
+      if (gy < d.H && gx < d.W)
+        *reinterpret_cast<uint4 *>(zg + ((size_t)gy * d.W + gx) * C + ch * 8) = *reinterpret_cast<const uint4 *>(smem + K::S_A2 + ch * K::P3 + p * 16);
+    }
+    // deterministic channel sums: warp = (chunk, pixel half), lanes stride the pixels, shuffle tree, 2 partials per chunk
+    float *red = reinterpret_cast<float *>(smem + K::S_X + K::X_RED);
+    for (int u = warp; u < K::KC2 * 2; u += kTcThreads / 32) {
+      const int ch = u % K::KC2, hf = u / K::KC2;
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      for (int p = hf * (K::M3 / 2) + lane; p < (hf + 1) * (K::M3 / 2); p += 32) {
+        const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
+        if (gy < d.H && gx < d.W) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A2 + ch * K::P3 + p * 16), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[hf * C + ch * 8 + i] = s[i];
+      }
+    }
+    __syncthreads();
+    if (tid < C) {
+      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = red[tid] + red[C + tid];
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512));
+  }
+}
+
+template <int C, bool SHIFT>
+static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st) {
+  using K = TcCfg<C, SHIFT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    attr_set = true;
+  }
+  static const ShiftTable tab = make_shift_table(C);
+  dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + K::TH - 1) / K::TH, d.T);
+  cab_pass_a_tc_kernel<C, SHIFT><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
+  count_launch();
+  return check_launch("cab_pass_a_tc");
+}
+
+int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st) {
+  if (d.C == 64) {
+    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false>(d, st);
+    return launch_pass_a_tc<64, true>(d, st);
+  }
+  set_error("cab_pass_a: C=%d unsupported (64)", d.C);
+  return GSN_E_UNSUPPORTED;
+}
+
+}  // namespace gsn

@@ -30,6 +30,27 @@ class Engine:
         self.sd = {k: v.detach().to(self.dev, torch.float32) for k, v in state_dict.items()}
         self.cache = {}
         self.boff = 1 if spec.denoise else 0
+        # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
+        self.timeline = None
+
+    def _timed(self, name, pixels):
+        """Context manager recording CUDA events around one launch on the launching stream (off unless profiling)."""
+        eng = self
+
+        class _T:
+            def __enter__(self_inner):
+                if eng.timeline is not None:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.b = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record(torch.cuda.current_stream(eng.dev))
+
+            def __exit__(self_inner, *exc):
+                if eng.timeline is not None:
+                    self_inner.b.record(torch.cuda.current_stream(eng.dev))
+                    eng.timeline.append((name, pixels, self_inner.a, self_inner.b))
+                return False
+
+        return _T()
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -87,7 +108,8 @@ class Engine:
         d.pixel_shuffle = 1 if pixel_shuffle else 0
         d.chan_partial = partial.data_ptr() if partial is not None else None
         d.dst = dst.data_ptr()
-        L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
+        with self._timed("conv_mma", T * Hout * Wout):
+            L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
         return (dst, partial) if want_sums else dst
 
     # ------------------------------------------------------------------ CAB (dense 3x3 + channel attention)
@@ -168,7 +190,8 @@ class Engine:
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
             a.debug_stage, a.debug_out = debug_stage, dbg.data_ptr()
-        L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
+        with self._timed("cab_pass_a_shift" if shift else "cab_pass_a", T * H * W):
+            L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
         weff = self._new(T, Cc * Cc)
         beff = self._new(T, Cc, dtype=torch.float32)
         L.check(self.lib.gsn_cab_fold(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["du0"].data_ptr(), fw["du2"].data_ptr(),
@@ -179,7 +202,8 @@ class Engine:
         b = L.CabPassB()
         b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, a.circular
         b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
-        L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
+        with self._timed("cab_pass_b", T * H * W):
+            L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
         if debug_stage:
             return out, z, dbg
         return out

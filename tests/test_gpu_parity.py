@@ -1,0 +1,266 @@
+"""GPU parity suite (-m gpu): every CUDA op and the whole net, called through the C-ABI, against the CPU oracle
+(same seeded inputs) and against the committed reference goldens.  Tolerances: activations are stored in fp16
+(2^-11 relative per stage, fp32 accumulation), so single ops must agree to ~1e-3 relative RMS and the whole net to
+>= 50 dB PSNR against the fp32 reference (the reference's own fp16 path reaches 66-68 dB)."""
+import dataclasses
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_io as gio
+
+sys.path.insert(0, os.path.join(gio.ROOT, "oracle"))
+import shiftnet_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda:0"
+
+
+def to_nhwc(x, cp=None):
+    """(T,C,H,W) fp32 cpu -> (T,H,W,Cp) fp16 cuda, zero padded channels."""
+    T, C, H, W = x.shape
+    cp = cp or (C + 15) // 16 * 16
+    out = torch.zeros(T, H, W, cp, dtype=torch.float16, device=DEV)
+    out[..., :C] = x.permute(0, 2, 3, 1).to(DEV).half()
+    return out
+
+
+def from_nhwc(t, c):
+    return t[..., :c].permute(0, 3, 1, 2).float().cpu()
+
+
+def rel_rms(a, ref):
+    return ((a - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+def check(a, ref, tol, what):
+    assert a.shape == ref.shape, (what, a.shape, ref.shape)
+    assert torch.isfinite(a).all(), what
+    r = rel_rms(a, ref)
+    m = (a - ref).abs().max().item()
+    print(f"[parity] {what}: rel_rms={r:.2e} max_abs={m:.2e} ref_rms={ref.pow(2).mean().sqrt().item():.3f}")
+    assert r < tol, (what, r, m)
+
+
+@pytest.fixture(scope="module")
+def env():
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
+    eng = gio.pkg("host.engine").Engine(spec, {k: v.to(DEV) for k, v in sd.items()}, DEV)
+    return sd, spec, eng, gio.load_golden("gshift_deblur2")
+
+
+# ------------------------------------------------------------------------------------------------ dense conv
+CONV_CASES = [
+    # name, src channels, cout, k, stride, pad, bias, prelu, residual, pixel_shuffle
+    ("3x3_14_14", [14], 14, 3, 1, 1, False, False, False, False),
+    ("3x3_s2_bias_14_18", [14], 18, 3, 2, 1, True, False, False, False),
+    ("1x1_22_18", [22], 18, 1, 1, 0, False, False, False, False),
+    ("2x2_s2_prelu_14_64", [14], 64, 2, 2, 0, False, True, False, False),
+    ("3x3_s2_bias_64_64", [64], 64, 3, 2, 1, True, False, False, False),
+    ("3x3_cat3_bias_14", [14, 14, 14], 14, 3, 1, 1, True, False, False, False),
+    ("3x3_res_14_14", [14], 14, 3, 1, 1, False, False, True, False),
+    ("3x3_shuffle_prelu_64_56", [64], 56, 3, 1, 1, True, True, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_mma(env, case):
+    _, _, eng, _ = env
+    name, srcs_c, cout, k, stride, pad, bias, prelu, residual, shuffle = case
+    g = torch.Generator().manual_seed(5)
+    T, H, W = 2, 20, 28                       # not multiples of the 16x16 tile
+    xs = [torch.randn(T, c, H, W, generator=g) for c in srcs_c]
+    w = torch.randn(cout, sum(srcs_c), k, k, generator=g) / (sum(srcs_c) * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    key = "test." + name
+    eng.sd[key + ".weight"] = w.to(DEV)
+    if bias:
+        eng.sd[key + ".bias"] = b.to(DEV)
+    eng.sd[key + ".slope"] = torch.tensor([0.2], device=DEV)
+    xq = [x.half().float() for x in xs]       # the kernel sees fp16-rounded inputs
+    ref = F.conv2d(torch.cat(xq, 1), w.half().float(), b, stride=stride, padding=pad)
+    if prelu:
+        ref = F.prelu(ref, torch.tensor([0.2]))
+    res_t = None
+    if residual:
+        r = torch.randn(ref.shape, generator=g)
+        res_t = to_nhwc(r)
+        ref = ref + r.half().float()
+    if shuffle:
+        ref = F.pixel_shuffle(ref, 2)
+    out = eng.conv(key, [to_nhwc(x) for x in xs], srcs_c, cout, stride=stride, pad=pad,
+                   prelu_key=key + ".slope" if prelu else None, residual=res_t, pixel_shuffle=shuffle)
+    torch.cuda.synchronize()
+    cr = cout // 4 if shuffle else cout
+    got = from_nhwc(out, cr)
+    check(got, ref, 2e-3, "conv " + name)
+    if out.shape[-1] > cr:
+        assert out[..., cr:].abs().max().item() == 0.0, "padding channels must stay zero"
+
+
+def test_conv_in_out(env):
+    sd, spec, eng, _ = env
+    P, L = gio.pkg("host.packing"), gio.pkg("host.lib")
+    import ctypes as C
+    g = torch.Generator().manual_seed(6)
+    T, H, W = 3, 20, 36
+    x = torch.rand(T, 3, H, W, generator=g)
+    for dt, tdt in ((L.DTYPE_F16, torch.float16), (L.DTYPE_F32, torch.float32)):
+        xd = x.to(DEV, tdt).contiguous()
+        wi, bi = P.pack_conv_in(eng.sd["feat_extract.0.weight"], eng.sd["feat_extract.0.bias"], 16)
+        f0 = torch.empty(T, H, W, 16, dtype=torch.float16, device=DEV)
+        L.check(eng.lib.gsn_conv_in(xd.data_ptr(), dt, T, 3, H, W, wi.data_ptr(), bi.data_ptr(), 16, f0.data_ptr(), eng._stream()))
+        ref = F.conv2d(xd.float().cpu(), sd["feat_extract.0.weight"], sd["feat_extract.0.bias"], padding=1)
+        check(from_nhwc(f0, 14), ref, 1.5e-3, f"conv_in dtype={dt}")
+        assert f0[..., 14:].abs().max().item() == 0.0
+        # conv_out: 5x5 14->3 + residual
+        feat = torch.randn(T, 14, H, W, generator=g)
+        wo = P.pack_conv_out(eng.sd["conv_last.weight"], 16)
+        out = torch.empty(T, 3, H, W, dtype=tdt, device=DEV)
+        fd = to_nhwc(feat)
+        L.check(eng.lib.gsn_conv_out(fd.data_ptr(), 16, 5, wo.data_ptr(), xd.data_ptr(), 3, dt, T, H, W, out.data_ptr(), eng._stream()))
+        ref = F.conv2d(feat.half().float(), sd["conv_last.weight"], None, padding=2) + xd.float().cpu()
+        check(out.float().cpu(), ref, 1.5e-3, f"conv_out dtype={dt}")
+
+
+def test_upsample_add(env):
+    _, _, eng, _ = env
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 18, 10, 14, generator=g)
+    skip = torch.randn(2, 18, 20, 28, generator=g)
+    out = torch.empty(2, 20, 28, 32, dtype=torch.float16, device=DEV)
+    xd, sk = to_nhwc(x), to_nhwc(skip)      # keep the device tensors alive across the async launch
+    gio.pkg("host.lib").check(eng.lib.gsn_upsample2x_add(xd.data_ptr(), sk.data_ptr(), out.data_ptr(), 2, 10, 14, 32, eng._stream()))
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.half().float(), scale_factor=2, mode="bilinear", align_corners=False) + skip.half().float()
+    check(from_nhwc(out, 18), ref, 1e-3, "upsample2x_add")
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+def test_cab(env):
+    sd, spec, eng, gold = env
+    x = gio.module_input("cab", spec)
+    out = from_nhwc(eng.cab("feat_extract.1", to_nhwc(x), spec.n0), spec.n0)
+    check(out, O.cab(sd, "feat_extract.1", x), 3e-3, "cab vs oracle")
+    check(out, torch.from_numpy(gold["cab"]), 3e-3, "cab vs reference golden")
+
+
+@pytest.mark.parametrize("which", ["cab2_fwd", "cab2_rev", "cab1"])
+@pytest.mark.parametrize("circular", [True, False])
+def test_gated_cab(env, which, circular):
+    sd, spec, eng, gold = env
+    L = gio.pkg("host.lib")
+    x = gio.module_input("shift", spec)
+    blk = "stage1.decoder_level1"
+    eng2 = gio.pkg("host.engine").Engine(dataclasses.replace(spec, circular=circular), {}, DEV)
+    eng2.sd = eng.sd
+    if which == "cab1":
+        p, mode = blk + ".encoder_level1.1", L.MODE_CAB1
+        ref = O.cab1(sd, p, x, False)
+    else:
+        rev = which == "cab2_rev"
+        p = blk + (".encoder_level1_1.0" if rev else ".encoder_level1.0")
+        mode = L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD
+        ref = O.cab2(sd, p, O.channel_shift(x, rev, circular), spec.c1, False)
+    out = from_nhwc(eng2.gated_cab(p, to_nhwc(x), mode), spec.c1)
+    check(out, ref, 3e-3, f"{which} circular={circular} vs oracle")
+    if circular:
+        check(out, torch.from_numpy(gold[which]), 3e-3, f"{which} vs reference golden")
+
+
+def test_gated_cab_ragged_sizes(env):
+    """H, W not multiples of the tile, T=1 and T=2 (wrap onto itself / neighbour is the only other frame)."""
+    sd, spec, eng, _ = env
+    L = gio.pkg("host.lib")
+    blk = "stage1.encoder_level2"
+    for T, H, W in ((1, 12, 20), (2, 9, 33), (3, 26, 18)):
+        g = torch.Generator().manual_seed(T * 100 + H)
+        x = 0.5 * torch.randn(T, spec.c1, H, W, generator=g)
+        for rev in (False, True):
+            p = blk + (".encoder_level1_1.0" if rev else ".encoder_level1.0")
+            ref = O.cab2(sd, p, O.channel_shift(x, rev, True), spec.c1, False)
+            out = from_nhwc(eng.gated_cab(p, to_nhwc(x), L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD), spec.c1)
+            check(out, ref, 3e-3, f"cab2 rev={rev} T={T} {H}x{W}")
+        ref = O.cab1(sd, blk + ".encoder_level1.1", x, False)
+        out = from_nhwc(eng.gated_cab(blk + ".encoder_level1.1", to_nhwc(x), L.MODE_CAB1), spec.c1)
+        check(out, ref, 3e-3, f"cab1 T={T} {H}x{W}")
+
+
+def test_shift_block(env):
+    sd, spec, eng, gold = env
+    x = gio.module_input("shift", spec)
+    out = from_nhwc(eng.shift_block("stage1.decoder_level1", to_nhwc(x)), spec.c1)
+    check(out, O.shift_block(sd, "stage1.decoder_level1", x, O.ARCHS[spec.name]), 5e-3, "shift block vs oracle")
+    check(out, torch.from_numpy(gold["block"]), 5e-3, "shift block vs reference golden")
+
+
+def test_tfr_unet(env):
+    sd, spec, eng, gold = env
+    x = gio.module_input("tfr", spec)
+    out = from_nhwc(eng.tfr_unet("orb1", to_nhwc(x)), spec.n0)
+    check(out, O.tfr_unet(sd, "orb1", x, O.ARCHS[spec.name]), 5e-3, "TFR_UNet vs oracle")
+    check(out, torch.from_numpy(gold["tfr"]), 5e-3, "TFR_UNet vs reference golden")
+
+
+def test_stage1(env):
+    sd, spec, eng, gold = env
+    x = gio.module_input("stage1", spec)
+    out = from_nhwc(eng.stage1("stage1", to_nhwc(x)), spec.n0)
+    check(out, torch.from_numpy(gold["stage1"]), 1e-2, "stage1 (Encoder2) vs reference golden")
+
+
+def _net(sd, dtype=torch.float16):
+    from basicsr.models.archs.gshift_deblur2 import GShiftNet
+    net = GShiftNet(future_frames=2, past_frames=2)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    return net.half() if dtype == torch.float16 else net
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_full_forward_golden(env, dtype):
+    """The drop-in call of inference/test_deblur_small.py:84-89,134 on the golden clip."""
+    sd, spec, _, gold = env
+    x, _ = gio.clip_input(spec)
+    out = _net(sd, dtype)(x.to(DEV, dtype))
+    assert out.dtype == dtype and tuple(out.shape) == (2, 3, 32, 40)
+    ref = torch.from_numpy(gold["full"])
+    p = O.psnr(out.float().cpu(), ref)
+    print(f"[parity] full forward {dtype}: PSNR vs reference fp32 = {p:.2f} dB")
+    assert p >= 50.0
+
+
+def test_full_forward_k1_config_vs_oracle(env):
+    """BASELINE config K1 (1x8x3x256x256): PSNR vs the fp32 oracle and the relative PSNR-vs-GT drift (<= 1e-3)."""
+    sd, spec, _, _ = env
+    gt, x = gio.pkg("host.synth").synthetic_clip(8, 256, 256)
+    ref = O.gshiftnet_forward(sd, O.ARCHS[spec.name], x)
+    out = _net(sd)(x.to(DEV).half()).float().cpu()
+    p = O.psnr(out, ref)
+    pg_ref, pg_out = O.psnr(ref.clamp(0, 1), gt[0, 2:-2]), O.psnr(out.clamp(0, 1), gt[0, 2:-2])
+    drift = abs(pg_out - pg_ref) / pg_ref
+    print(f"[parity] K1 256x256 T=8: PSNR(cuda, oracle)={p:.2f} dB ; PSNR-vs-GT ref={pg_ref:.4f} ours={pg_out:.4f} drift={drift:.2e}")
+    assert p >= 50.0 and drift <= 1e-3
+
+
+def test_full_size_cyclic_frame_equivariance(env):
+    """Size-independent property at 720p: with the circular temporal roll of Ours-s every op is equivariant to a cyclic
+    shift of the frames, so forward(roll(x, 1))[i] == forward(x)[i-1] bit-exactly on the overlapping output frames."""
+    sd, spec, _, _ = env
+    net = _net(sd)
+    g = torch.Generator().manual_seed(3)
+    T, H, W = 7, 720, 1280
+    x = torch.rand(1, T, 3, H, W, generator=g).to(DEV).half()
+    a = net(x)
+    b = net(torch.roll(x, 1, dims=1))
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all()
+    # a[i] is frame i+2 of x ; b[i] is frame i+2 of roll(x) = frame i+1 of x  => b[i+1] == a[i]
+    assert torch.equal(b[1:], a[:-1])
+    # and the run is deterministic
+    assert torch.equal(net(x), a)
