@@ -173,11 +173,15 @@ def main():
     sampler.start()
     l0 = lib.gsn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("GSN_NCU_RANGE") == "1":      # ncu --profile-from-start off: capture exactly the timed steps
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         out = net(x_dev)
     e1.record()
     barrier()
+    if os.environ.get("GSN_NCU_RANGE") == "1":
+        torch.cuda.profiler.stop()
     launches = lib.gsn_launch_count() - l0
     ms = e0.elapsed_time(e1) / args.steps
 
