@@ -1,0 +1,41 @@
+"""Per-stage clock64() breakdown of the tcgen05 pass A (debug_stage=9).  Run on the GPU box."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import golden_io as gio
+
+L = gio.pkg("host.lib")
+sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
+eng = gio.pkg("host.engine").Engine(spec, {k: v.cuda() for k, v in sd.items()}, "cuda")
+T, H, W = 20, 360, 640
+x = (0.5 * torch.randn(T, H, W, 64, device="cuda")).half()
+names = {True: ["start", "loads", "gather", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"],
+         False: ["start", "loads", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]}
+for p, mode in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD), ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1)):
+    shift = mode != L.MODE_CAB1
+    blob = gio.pkg("host.packing").pack_cab_pass_a(eng.sd, p, 64, shift, 0)
+    nt = eng.lib.gsn_cab_tiles(mode, H, W)
+    z = torch.empty_like(x)
+    part = torch.empty(T, nt, 64, device="cuda")
+    dbg = torch.zeros(T * nt * 16, dtype=torch.int64, device="cuda")
+    a = L.CabPassA()
+    a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, 64, mode, 1
+    a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), part.data_ptr()
+    a.debug_stage, a.debug_out = 9, dbg.data_ptr()
+    for _ in range(2):
+        L.check(eng.lib.gsn_cab_pass_a(C.byref(a), eng._stream()))
+    torch.cuda.synchronize()
+    c = dbg.view(T * nt, 16).double()
+    n = len(names[shift])
+    d = (c[:, 1:n] - c[:, :n - 1])
+    tot = (c[:, n - 1] - c[:, 0])
+    print(f"mode={'shift' if shift else 'cab1'} tiles={T*nt} mean cycles/tile={tot.mean().item():.0f} (min {tot.min().item():.0f} max {tot.max().item():.0f})")
+    for i in range(n - 1):
+        print(f"   {names[shift][i+1]:12s} {d[:, i].mean().item():8.0f}  ({100 * d[:, i].mean().item() / tot.mean().item():4.1f}%)")

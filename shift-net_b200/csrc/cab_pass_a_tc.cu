@@ -79,6 +79,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5 with the single-MUFU tanh.approx (rel. error 2^-11, i.e. below the fp16 rounding of z);
+// the exp+rcp form costs two MUFU ops per element and made the gate stage SFU-bound (2048 of 2350 cycles per tile).
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(t, 0.5f, 0.5f);
+}
+
 // ---- packed half helpers --------------------------------------------------------------------------
 struct H8 {
   __half2 h[4];
@@ -174,6 +182,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
   const size_t frame = (size_t)d.H * d.W * C;
   const uint32_t bar = smem_u32(smem + K::S_X + K::X_BAR);
+  // debug_stage == 9: thread 0 of every CTA records clock64() at the stage boundaries (profiling aid, tests only)
+  long long *clk = (d.debug_stage == 9 && tid == 0)
+                       ? reinterpret_cast<long long *>(d.debug_out) + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16
+                       : nullptr;
+  int clk_i = 0;
+#define GSN_CLK() do { if (clk) clk[clk_i++] = clock64(); } while (0)
+  GSN_CLK();
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + K::S_X + K::X_TMEM);
 
   // ---- P0: async loads (small params, W1, gather box), TMEM allocation, barrier init ---------------
@@ -188,12 +203,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       const bool fwd = d.mode == GSN_MODE_CAB2_FWD;
       const __half *src = xg + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
       constexpr int CH = K::HC / 8;
-      for (int i = tid; i < K::BW * K::BH * CH; i += kTcThreads) {
-        const int ch = i % CH, p = i / CH, by = p / K::BW, bx = p - by * K::BW;
+      for (int p = tid; p < K::BW * K::BH; p += kTcThreads) {   // one box pixel (CH x 16 B) per thread-iteration
+        const int by = p / K::BW, bx = p - by * K::BW;
         const int gy = y0 - 12 + by, gx = x0 - 12 + bx;
         const bool valid = gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
-        const __half *sp = valid ? src + ((size_t)gy * d.W + gx) * C + ch * 8 : src;
-        cp_async16(smem + K::S_R + (size_t)p * K::HC * 2 + ch * 16, sp, valid);
+        const __half *sp = valid ? src + ((size_t)gy * d.W + gx) * C : src;
+        unsigned char *dp = smem + K::S_R + (size_t)p * K::HC * 2;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) cp_async16(dp + ch * 16, sp + (valid ? ch * 8 : 0), valid);
       }
     } else {
       for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
@@ -213,62 +230,85 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     tc_fence_after();
   }
   const uint32_t tmem = *tmem_slot;
+  GSN_CLK();  // 1: loads landed
 
   // ---- P1a (SHIFT): per-channel spatial-shift gather fused with conv1 (dw3x3, zero pad) -> raw A1 planes --------
   if (SHIFT) {
     const __half *wc1 = reinterpret_cast<const __half *>(smem + K::S_X + K::X_C1);
     const __half *r12 = reinterpret_cast<const __half *>(smem + K::S_R);
     constexpr int SEG = K::R1W / 2;  // 11-pixel row segments
+    // destination positions of the shifted tensor touched by this tile: rows y0-4 .. y0+TH+3, cols x0-4 .. x0+TW+3
+    const bool interior = y0 >= 4 && y0 + K::TH + 4 <= d.H && x0 >= 4 && x0 + K::TW + 4 <= d.W;
     for (int item = tid; item < K::HC * K::R1H * 2; item += kTcThreads) {
       const int c = item % K::HC, rest = item / K::HC;
       const int ry = rest % K::R1H, seg = rest / K::R1H;
-      const int dy = tab.dy[c], dx = tab.dx[c];
+      int dy, dx;
+      shift_offset<C>(c, dy, dx);
       const int gy = y0 - 3 + ry;
       float w[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) w[i] = __half2float(wc1[i * K::HC + c]);
-      bool rowok[3];
-      int rowoff[3];
-#pragma unroll
-      for (int ty = 0; ty < 3; ++ty) {
-        const int sy = gy + ty - 1;                         // row in the shifted tensor: must be inside the image
-        rowok[ty] = sy >= 0 && sy < d.H;
-        rowoff[ty] = (ry + ty - 1 - dy + 9) * K::BW - dx + 9;  // + column gives the source pixel inside the box
-      }
       const int rx0 = seg * SEG;
-      float v[3][3];
-      auto load_col = [&](int col, float(&o)[3]) {        // col = region column of the shifted tensor
-        const int sx = x0 - 3 + col;
-        const bool cok = sx >= 0 && sx < d.W;
-#pragma unroll
-        for (int ty = 0; ty < 3; ++ty)
-          o[ty] = (cok && rowok[ty]) ? __half2float(r12[(rowoff[ty] + col) * K::HC + c]) : 0.f;
-      };
-      {
-        float a[3], b[3];
-        load_col(rx0 - 1, a);
-        load_col(rx0, b);
-#pragma unroll
-        for (int ty = 0; ty < 3; ++ty) { v[ty][0] = 0.f; v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
-      }
+      // source of (shifted row ry+ty-1, shifted col) inside the box: ((ry+ty-1-dy+9)*BW + col-dx+9)
+      const __half *rp = r12 + ((ry - 1 - dy + 9) * K::BW - dx + 9) * K::HC + c;
       unsigned char *dstp = smem + K::S_A1 + (C / 8 + c / 8) * K::P1 + (c & 7) * 2;
-#pragma unroll
-      for (int i = 0; i < SEG; ++i) {
-        const int rx = rx0 + i;
-        float nc[3];
-        load_col(rx + 1, nc);
-        float acc = 0.f;
+      float v[3][3];
+      if (interior) {
 #pragma unroll
         for (int ty = 0; ty < 3; ++ty) {
-          v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty];
-          acc = fmaf(v[ty][0], w[ty * 3 + 0], acc);
-          acc = fmaf(v[ty][1], w[ty * 3 + 1], acc);
-          acc = fmaf(v[ty][2], w[ty * 3 + 2], acc);
+          v[ty][1] = __half2float(rp[(ty * K::BW + rx0 - 1) * K::HC]);
+          v[ty][2] = __half2float(rp[(ty * K::BW + rx0) * K::HC]);
         }
-        *reinterpret_cast<__half *>(dstp + (ry * K::R1W + rx) * 16) = __float2half_rn(acc);
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+          const int rx = rx0 + i;
+          float acc = 0.f;
+#pragma unroll
+          for (int ty = 0; ty < 3; ++ty) {
+            v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2];
+            v[ty][2] = __half2float(rp[(ty * K::BW + rx + 1) * K::HC]);
+            acc = fmaf(v[ty][0], w[ty * 3 + 0], acc);
+            acc = fmaf(v[ty][1], w[ty * 3 + 1], acc);
+            acc = fmaf(v[ty][2], w[ty * 3 + 2], acc);
+          }
+          *reinterpret_cast<__half *>(dstp + (ry * K::R1W + rx) * 16) = __float2half_rn(acc);
+        }
+      } else {
+        bool rowok[3];
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) { const int sy = gy + ty - 1; rowok[ty] = sy >= 0 && sy < d.H; }
+        auto load_col = [&](int col, float(&o)[3]) {      // col = region column of the shifted tensor (dest must be in-image)
+          const int sx = x0 - 3 + col;
+          const bool cok = sx >= 0 && sx < d.W;
+#pragma unroll
+          for (int ty = 0; ty < 3; ++ty) o[ty] = (cok && rowok[ty]) ? __half2float(rp[(ty * K::BW + col) * K::HC]) : 0.f;
+        };
+        {
+          float a[3], b[3];
+          load_col(rx0 - 1, a);
+          load_col(rx0, b);
+#pragma unroll
+          for (int ty = 0; ty < 3; ++ty) { v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+        }
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+          const int rx = rx0 + i;
+          float nc[3];
+          load_col(rx + 1, nc);
+          float acc = 0.f;
+#pragma unroll
+          for (int ty = 0; ty < 3; ++ty) {
+            v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty];
+            acc = fmaf(v[ty][0], w[ty * 3 + 0], acc);
+            acc = fmaf(v[ty][1], w[ty * 3 + 1], acc);
+            acc = fmaf(v[ty][2], w[ty * 3 + 2], acc);
+          }
+          *reinterpret_cast<__half *>(dstp + (ry * K::R1W + rx) * 16) = __float2half_rn(acc);
+        }
       }
     }
     __syncthreads();
+    GSN_CLK();  // 2: gather done (SHIFT only)
     // the gather box is dead now: stream the phase-2 weights (dw taps + W2) into its tail
     for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
     cp_async_commit();
@@ -280,54 +320,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     const float *ln_b = ln_g + K::CIN;
     constexpr int NV = SHIFT ? 24 : 16;
     constexpr int ITEMS = (K::M1 + 7) / 8 * 8 * 4;   // whole warps only (quad shuffles below)
-    for (int item = tid; item < ITEMS; item += kTcThreads) {
-      const int q = item >> 2, j = item & 3;
+    constexpr int NIT = (ITEMS + kTcThreads - 1) / kTcThreads;
+    const int j = tid & 3;                            // the quad lane never changes across a thread's items
+    int chunk_of[NV / 8];
+    if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
+    else { chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1; }
+    float gam[NV], bet[NV];
+#pragma unroll
+    for (int k = 0; k < NV / 8; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { gam[k * 8 + i] = ln_g[chunk_of[k] * 8 + i]; bet[k * 8 + i] = ln_b[chunk_of[k] * 8 + i]; }
+    uint4 raw[NIT][2];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {               // issue every global load first (memory-level parallelism)
+      const int q = (tid + it * kTcThreads) >> 2;
       const int ry = q / K::R1W, rx = q - ry * K::R1W;
       const int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
       const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
-      float v[NV];
-      int chunk_of[NV / 8];
-      if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
-      else { chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1; }
+      raw[it][0] = raw[it][1] = make_uint4(0, 0, 0, 0);
       if (inimg) {
         const size_t pix = ((size_t)gy * d.W + gx) * C;
         if (SHIFT) {
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8)), *reinterpret_cast<float(*)[8]>(&v[0]));
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
-          unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A1 + (C / 8 + j) * K::P1 + q * 16), *reinterpret_cast<float(*)[8]>(&v[16]));
+          raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8));
+          raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8));
         } else {
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16)), *reinterpret_cast<float(*)[8]>(&v[0]));
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
+          raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16));
+          raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8));
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = 0.f;
       }
-      float s = 0.f;
+    }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) s += v[i];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      const float mu = s * (1.f / K::CIN);
-      float ss = 0.f;
+    for (int it = 0; it < NIT; ++it) {
+      const int item = tid + it * kTcThreads;
+      if (item < ITEMS) {                            // warp-uniform (ITEMS is a multiple of 32)
+        const int q = item >> 2;
+        const int ry = q / K::R1W, rx = q - ry * K::R1W;
+        const int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
+        const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
+        float v[NV];
+        unpack8(raw[it][0], *reinterpret_cast<float(*)[8]>(&v[0]));
+        unpack8(raw[it][1], *reinterpret_cast<float(*)[8]>(&v[8]));
+        if (SHIFT) {
+          if (inimg) unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A1 + (C / 8 + j) * K::P1 + q * 16), *reinterpret_cast<float(*)[8]>(&v[16]));
+          else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      const float rstd = rsqrtf(ss * (1.f / K::CIN) + 1e-6f);
-      if (q < K::M1) {
+            for (int i = 16; i < NV; ++i) v[i] = 0.f;
+          }
+        }
+        float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV / 8; ++k) {
-          float o[8];
-          const int cbase = chunk_of[k] * 8;
+        for (int i = 0; i < NV; ++i) s += v[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float mu = s * (1.f / K::CIN);
+        float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = inimg ? (v[k * 8 + i] - mu) * rstd * ln_g[cbase + i] + ln_b[cbase + i] : 0.f;
-          *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
+        for (int i = 0; i < NV; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        const float rstd = inimg ? rsqrtf(ss * (1.f / K::CIN) + 1e-6f) : 0.f;   // rstd = 0 and beta masked => zero row
+        if (q < K::M1) {
+#pragma unroll
+          for (int k = 0; k < NV / 8; ++k) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = rstd * gam[k * 8 + i];
+              o[i] = fmaf(v[k * 8 + i], a, (inimg ? bet[k * 8 + i] : 0.f) - mu * a);
+            }
+            *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
+          }
         }
       }
     }
     fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
     __syncthreads();
+    GSN_CLK();  // LN done
   }
   if (d.debug_stage == 1) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
@@ -356,6 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   mbar_wait(bar, 0);
   tc_fence_after();
   __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
+  GSN_CLK();  // GEMM1 done
 
   // ---- P3: TMEM -> fp16 G1 planes (all 2C channels of the region) ----------------------------------------------
   {
@@ -379,6 +448,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     tc_fence_before();
     __syncthreads();
+    GSN_CLK();  // TMEM -> G1 done
   }
 
   // ---- P4: dw3x3 + id on both halves, SimpleGate -> GATED (zero outside the image) ---------------------------------
@@ -433,6 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       }
     }
     __syncthreads();
+    GSN_CLK();  // dwA done
   }
   if (d.debug_stage == 2) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
@@ -496,6 +567,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     fence_async_proxy();
     __syncthreads();
+    GSN_CLK();  // dwB done
   }
   if (d.debug_stage == 3) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
@@ -522,6 +594,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   mbar_wait(bar, 1);
   tc_fence_after();
   __syncthreads();                 // A2 is dead: its space becomes the z staging tile
+  GSN_CLK();  // GEMM2 done
 
   // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store + per-tile channel sums ---
   {
@@ -537,12 +610,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       for (int c4 = 0; c4 < 4; ++c4) {
         float z[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = __uint_as_float(a[c4 * 8 + i]) * sigmoidf_fast(__uint_as_float(b[c4 * 8 + i]));
+        for (int i = 0; i < 8; ++i) z[i] = __uint_as_float(a[c4 * 8 + i]) * sigmoid_tanh(__uint_as_float(b[c4 * 8 + i]));
         *reinterpret_cast<uint4 *>(smem + K::S_A2 + (cg * 4 + c4) * K::P3 + px * 16) = pack8(z);
       }
     }
     tc_fence_before();
     __syncthreads();
+    GSN_CLK();  // gate2 -> z tile done
     __half *zg = reinterpret_cast<__half *>(d.z) + (size_t)t * frame;
     for (int i = tid; i < K::M3 * K::KC2; i += kTcThreads) {
       const int ch = i % K::KC2, p = i / K::KC2;
@@ -582,6 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = red[tid] + red[C + tid];
     }
   }
+  GSN_CLK();  // stores + sums done
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512));
   }

@@ -13,8 +13,9 @@
 
 namespace gsn {
 
-template <int NT>
-__global__ void __launch_bounds__(256) conv_mma_kernel(const GsnConvDesc d, int IH, int IW, int pitch) {
+template <int NT, int KS, int STRIDE>
+__global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const GsnConvDesc d, int pitch) {
+  constexpr int IH = 15 * STRIDE + KS, IW = IH;   // compile-time tile geometry: no runtime integer divisions below
   extern __shared__ __align__(16) unsigned char smem[];
   __half *tile = reinterpret_cast<__half *>(smem);
   float *red = reinterpret_cast<float *>(smem + (size_t)IH * IW * pitch * 2);
@@ -22,25 +23,26 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const GsnConvDesc d, int 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.z;
   const int ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16;
-  const int ix0 = ox0 * d.stride - d.pad, iy0 = oy0 * d.stride - d.pad;
+  const int ix0 = ox0 * STRIDE - d.pad, iy0 = oy0 * STRIDE - d.pad;
 
   // ---- stage the input tile ---------------------------------------------------------------------
   {
     const int chunks = d.cin_p >> 3;
-    const int total = IH * IW * chunks;
     const int c1 = d.src_c[0], c2 = d.src_c[0] + d.src_c[1];
-    for (int i = tid; i < total; i += 256) {
-      const int ch = i % chunks, px = i / chunks;
+    for (int px = tid; px < IH * IW; px += 256) {
       const int ly = px / IW, lx = px - ly * IW;
       const int gy = iy0 + ly, gx = ix0 + lx;
       const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
-      const int c = ch * 8;
-      int s = 0, cb = 0;
-      if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
-      else if (c >= c1 && d.n_src > 1) { s = 1; cb = c1; }
-      const __half *base = reinterpret_cast<const __half *>(d.src[s]);
-      const __half *sp = valid ? base + (((size_t)t * d.Hin + gy) * d.Win + gx) * d.src_c[s] + (c - cb) : base;
-      cp_async16(tile + (size_t)px * pitch + c, sp, valid);
+      const size_t gpix = valid ? ((size_t)t * d.Hin + gy) * d.Win + gx : 0;
+      __half *dp = tile + (size_t)px * pitch;
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int c = ch * 8;
+        int s = 0, cb = 0;
+        if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
+        else if (c >= c1 && d.n_src > 1) { s = 1; cb = c1; }
+        const __half *base = reinterpret_cast<const __half *>(d.src[s]);
+        cp_async16(dp + c, valid ? base + gpix * d.src_c[s] + (c - cb) : base, valid);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -61,16 +63,17 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const GsnConvDesc d, int 
   const int ksteps = d.cin_p >> 4;
   const uint2 *wp = reinterpret_cast<const uint2 *>(d.wpack);
   const uint32_t tile_s = smem_u32(tile);
-  const int taps = d.ks * d.ks;
+  constexpr int taps = KS * KS;
 
+#pragma unroll 1
   for (int tap = 0; tap < taps; ++tap) {
-    const int ky = tap / d.ks, kx = tap - ky * d.ks;
-    const int ix = arow * d.stride + kx;
+    const int ky = tap / KS, kx = tap - ky * KS;
+    const int ix = arow * STRIDE + kx;
     for (int k = 0; k < ksteps; ++k) {
       uint32_t a[2][4];
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
-        const int iy = (2 * warp + m) * d.stride + ky;
+        const int iy = (2 * warp + m) * STRIDE + ky;
         const uint32_t addr = tile_s + (uint32_t)(((iy * IW + ix) * pitch + k * 16 + akof) * 2);
         ldmatrix_x4(a[m][0], a[m][1], a[m][2], a[m][3], addr);
       }
@@ -151,21 +154,31 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const GsnConvDesc d, int 
   }
 }
 
-template <int NT>
+template <int NT, int KS, int STRIDE>
 static int launch_conv(const GsnConvDesc &d, cudaStream_t st) {
-  const int IH = 15 * d.stride + d.ks, IW = IH;
+  constexpr int IH = 15 * STRIDE + KS, IW = IH;
   const int pitch = d.cin_p + 8;
   const size_t smem = (size_t)IH * IW * pitch * 2 + 8 * d.cout_p * sizeof(float);
   if (smem > 227 * 1024) { set_error("conv_mma: tile needs %zu B smem", smem); return GSN_E_UNSUPPORTED; }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<NT, KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   dim3 grid((d.Wout + 15) / 16, (d.Hout + 15) / 16, d.T);
-  conv_mma_kernel<NT><<<grid, 256, smem, st>>>(d, IH, IW, pitch);
+  conv_mma_kernel<NT, KS, STRIDE><<<grid, 256, smem, st>>>(d, pitch);
   count_launch();
   return check_launch("conv_mma");
+}
+
+template <int NT>
+static int launch_conv_nt(const GsnConvDesc &d, cudaStream_t st) {
+  if (d.ks == 3 && d.stride == 1) return launch_conv<NT, 3, 1>(d, st);
+  if (d.ks == 3 && d.stride == 2) return launch_conv<NT, 3, 2>(d, st);
+  if (d.ks == 1 && d.stride == 1) return launch_conv<NT, 1, 1>(d, st);
+  if (d.ks == 2 && d.stride == 2) return launch_conv<NT, 2, 2>(d, st);
+  set_error("conv_mma: ks=%d stride=%d unsupported (3/1, 3/2, 1/1, 2/2)", d.ks, d.stride);
+  return GSN_E_UNSUPPORTED;
 }
 
 }  // namespace gsn
@@ -192,11 +205,11 @@ extern "C" int gsn_conv_mma(const GsnConvDesc *dp, void *stream) {
   GSN_REQUIRE(!d.pixel_shuffle || (d.cout_p % 4 == 0 && !d.residual && !d.chan_partial), "conv_mma: bad pixel_shuffle combination");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (d.cout_p) {
-    case 16: return launch_conv<2>(d, st);
-    case 32: return launch_conv<4>(d, st);
-    case 48: return launch_conv<6>(d, st);
-    case 64: return launch_conv<8>(d, st);
-    case 80: return launch_conv<10>(d, st);
+    case 16: return launch_conv_nt<2>(d, st);
+    case 32: return launch_conv_nt<4>(d, st);
+    case 48: return launch_conv_nt<6>(d, st);
+    case 64: return launch_conv_nt<8>(d, st);
+    case 80: return launch_conv_nt<10>(d, st);
     default: set_error("conv_mma: cout_p=%d unsupported (16/32/48/64/80)", d.cout_p); return GSN_E_UNSUPPORTED;
   }
 }

@@ -13,17 +13,27 @@ static int grid_for(long long work_items, int block) {
 }
 
 // s[t][c] = sigmoid(W2 relu(W1 mean)), mean from deterministic per-tile partial sums (CALayer, d2:54-71)
-__global__ void __launch_bounds__(128) ca_scale_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
+__global__ void __launch_bounds__(256) ca_scale_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
                                                        const float *__restrict__ w1, const float *__restrict__ w2, int c,
                                                        int cr, int cp, float *__restrict__ s) {
+  __shared__ float part[256];
   __shared__ float mean[128];
   __shared__ float hid[128];
   const int t = blockIdx.x, tid = threadIdx.x;
-  if (tid < cp) {
+  {  // deterministic two-level reduction of the per-tile sums: 256/cp slices of the tile list, then a fixed-order sum
+    const int nparts = 256 / cp, ch = tid % cp, pi = tid / cp;
     float a = 0.f;
-    const float *p = partial + (size_t)t * ntiles * cp + tid;
-    for (int i = 0; i < ntiles; ++i) a += p[(size_t)i * cp];
-    mean[tid] = a * inv_hw;
+    if (pi < nparts) {
+      const float *p = partial + (size_t)t * ntiles * cp + ch;
+      for (int i = pi; i < ntiles; i += nparts) a += p[(size_t)i * cp];
+    }
+    part[tid] = a;
+    __syncthreads();
+    if (tid < cp) {
+      float m = 0.f;
+      for (int q = 0; q < nparts; ++q) m += part[q * cp + tid];
+      mean[tid] = m * inv_hw;
+    }
   }
   __syncthreads();
   if (tid < cr) {
@@ -117,7 +127,7 @@ extern "C" int gsn_ca_scale(const float *partial, int ntiles, float inv_hw, cons
   using namespace gsn;
   GSN_REQUIRE(partial && w1 && w2 && s, "ca_scale: null pointer");
   GSN_REQUIRE(c > 0 && c <= cp && cp <= 128 && cr > 0 && cr <= 128 && ntiles > 0 && T > 0, "ca_scale: bad sizes c=%d cr=%d cp=%d", c, cr, cp);
-  ca_scale_kernel<<<T, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, ntiles, inv_hw, w1, w2, c, cr, cp, s);
+  ca_scale_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, ntiles, inv_hw, w1, w2, c, cr, cp, s);
   count_launch();
   return check_launch("ca_scale");
 }

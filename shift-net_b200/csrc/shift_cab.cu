@@ -365,13 +365,22 @@ __global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__
                                                        int cr, const float *__restrict__ w3, const float *__restrict__ beta,
                                                        const float *__restrict__ bias3, int C, __half *__restrict__ weff,
                                                        float *__restrict__ beff) {
-  __shared__ float mean[128], hid[128], sc[128];
+  __shared__ float mean[128], hid[128], sc[128], part[256];
   const int t = blockIdx.x, tid = threadIdx.x;
-  if (tid < C) {
+  {  // deterministic two-level reduction of the per-tile channel sums
+    const int nparts = 256 / C, ch = tid % C, pi = tid / C;
     float a = 0.f;
-    const float *p = partial + (size_t)t * ntiles * C + tid;
-    for (int i = 0; i < ntiles; ++i) a += p[(size_t)i * C];
-    mean[tid] = a * inv_hw;
+    if (pi < nparts) {
+      const float *p = partial + (size_t)t * ntiles * C + ch;
+      for (int i = pi; i < ntiles; i += nparts) a += p[(size_t)i * C];
+    }
+    part[tid] = a;
+    __syncthreads();
+    if (tid < C) {
+      float m = 0.f;
+      for (int q = 0; q < nparts; ++q) m += part[q * C + tid];
+      mean[tid] = m * inv_hw;
+    }
   }
   __syncthreads();
   if (tid < cr) {

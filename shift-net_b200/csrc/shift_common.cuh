@@ -4,6 +4,17 @@
 
 namespace gsn {
 
+// Device-side lookup of the same table (constant bank, no per-kernel parameter copy).
+static __constant__ int8_t kShiftOuter[16][2] = {{8, 8}, {8, 4}, {8, 0}, {8, -4}, {8, -8}, {-8, 8}, {-8, 4}, {-8, 0}, {-8, -4},
+                                                 {-8, -8}, {4, 8}, {4, -8}, {0, 8}, {0, -8}, {-4, 8}, {-4, -8}};
+static __constant__ int8_t kShiftInner[8][2] = {{4, 4}, {4, 0}, {4, -4}, {0, 4}, {0, -4}, {-4, 4}, {-4, 0}, {-4, -4}};
+template <int C>
+__device__ __forceinline__ void shift_offset(int c, int &dy, int &dx) {
+  constexpr int number = C / 2 / 8, n2 = (number - 1) / 2, n1 = number - 2 * n2;
+  if (c < 16 * n2) { const int g = c / n2; dy = kShiftOuter[g][0]; dx = kShiftOuter[g][1]; }
+  else { const int g = (c - 16 * n2) / n1; dy = kShiftInner[g][0]; dx = kShiftInner[g][1]; }
+}
+
 struct ShiftTable {
   int8_t dy[40];
   int8_t dx[40];

@@ -25,14 +25,19 @@ class GShiftNetB200(nn.Module):
         self.num_fb = spec.default_ctx if past_frames is None else past_frames
         build_param_tree(self, spec)
         self._engine = None
+        self._graphs = {}
+        # Replay the whole forward (~740 kernel launches) as one CUDA graph per input shape: removes the launch gaps
+        # between the many short kernels.  Set GSN_CUDA_GRAPH=0 to launch eagerly (profiling per-kernel, debugging).
+        import os
+        self.use_cuda_graph = os.environ.get("GSN_CUDA_GRAPH", "1") != "0"
 
     # any change of the parameters invalidates the packed device weights
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._engine, self._graphs = None, {}
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self._engine, self._graphs = None, {}
         return super().load_state_dict(*a, **k)
 
     def engine(self):
@@ -48,7 +53,28 @@ class GShiftNetB200(nn.Module):
             raise RuntimeError("shiftnet_b200.GShiftNet runs on CUDA (B200, sm_100a) only; there is no CPU fallback")
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input are on different devices; call net.to(device) first")
-        return self.engine().forward(x, noise_map, past=self.num_fb, future=self.num_ff)
+        eng = self.engine()
+        if not self.use_cuda_graph or eng.timeline is not None or torch.cuda.is_current_stream_capturing():
+            return eng.forward(x, noise_map, past=self.num_fb, future=self.num_ff)
+        key = (tuple(x.shape), x.dtype, None if noise_map is None else tuple(noise_map.shape), self.num_fb, self.num_ff)
+        ent = self._graphs.get(key)
+        if ent is None:
+            # eager warm-up (packs weights, sets kernel attributes, primes the allocator), then capture
+            xs = x.clone()
+            ns = None if noise_map is None else noise_map.expand(noise_map.shape).clone()
+            eng.forward(xs, ns, past=self.num_fb, future=self.num_ff)
+            torch.cuda.synchronize(x.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out_s = eng.forward(xs, ns, past=self.num_fb, future=self.num_ff)
+            ent = (g, xs, ns, out_s)
+            self._graphs = {key: ent}            # keep one shape at a time (activations of a 720p clip are several GB)
+        g, xs, ns, out_s = ent
+        xs.copy_(x)
+        if ns is not None:
+            ns.copy_(noise_map)
+        g.replay()
+        return out_s.clone()
 
 
 def make_arch(arch_name):
