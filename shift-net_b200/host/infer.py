@@ -1,0 +1,234 @@
+"""Evaluation loop behind the ``inference/test_*.py`` entry points (reference: inference/test_deblur_small.py:51-177,
+inference/test_denoise_small.py:51-224), re-designed around the B200 path:
+
+* same CLI, chunking rules, metrics and log-line formats as the reference scripts;
+* work units (video, chunk) are sharded round-robin across the ranks of a ``torchrun`` launch (one process per GPU),
+  weights replicated, no communication during the forward; ONE all_gather (NCCL on GPUs, gloo on CPU tests) of the
+  per-frame (video, frame, psnr, ssim) records at the end so rank 0 prints the per-video / total averages;
+* frames come from disk (imageio or cv2) or, when no dataset is present (``--synthetic``), from a seeded generator.
+"""
+from __future__ import annotations
+
+import glob
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+
+class TraverseLogger:
+    def __init__(self, result_dir, filename="inference_log.txt", enabled=True):
+        self.enabled = enabled
+        self.f = open(os.path.join(result_dir, filename), "a") if enabled else None
+
+    def write_log(self, log):
+        if self.enabled:
+            print(log, flush=True)
+            self.f.write(log + "\n")
+            self.f.flush()
+
+
+def psnr_255(out, gt):
+    """skimage.metrics.peak_signal_noise_ratio(out, gt, data_range=255) restated (float64 MSE)."""
+    mse = np.mean((np.asarray(out, dtype=np.float64) - np.asarray(gt, dtype=np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10.0 * math.log10(255.0 ** 2 / mse)
+
+
+def ssim_calculate(img1, img2, sd=1.5, C1=0.01 ** 2, C2=0.03 ** 2):
+    """Gaussian-window SSIM on /255 CHW float32 (inference/test_deblur_small.py:25-49)."""
+    from scipy.ndimage import gaussian_filter
+    a = (np.array(img1, dtype=np.float32) / 255).transpose((2, 0, 1))
+    b = (np.array(img2, dtype=np.float32) / 255).transpose((2, 0, 1))
+    mu1, mu2 = gaussian_filter(a, sd), gaussian_filter(b, sd)
+    s1 = gaussian_filter(a * a, sd) - mu1 * mu1
+    s2 = gaussian_filter(b * b, sd) - mu2 * mu2
+    s12 = gaussian_filter(a * b, sd) - mu1 * mu2
+    return float(np.mean(((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))))
+
+
+def _imread(path):
+    try:
+        import imageio
+        return np.asarray(imageio.imread(path))
+    except ImportError:
+        import cv2
+        return cv2.imread(path, cv2.IMREAD_COLOR)[..., ::-1]
+
+
+def synthetic_videos(n_videos, n_frames, h, w, seed=0):
+    """{name: (blurred/noisy-free inputs uint8 list, gt uint8 list)} -- smooth random frames (no dataset offline)."""
+    out = {}
+    for v in range(n_videos):
+        g = torch.Generator().manual_seed(seed + v)
+        gt = torch.rand(n_frames, 3, h, w, generator=g)
+        gt = torch.nn.functional.avg_pool2d(gt, 5, 1, 2, count_include_pad=False)
+        blur = torch.nn.functional.avg_pool2d(gt, 3, 1, 1, count_include_pad=False)
+        to_u8 = lambda t: [(f.permute(1, 2, 0) * 255).round().clamp(0, 255).byte().numpy() for f in t]
+        out[f"syn{v:03d}"] = (to_u8(blur), to_u8(gt))
+    return out
+
+
+def plan_units(videos, task, one_len):
+    """[(video, kk, in_frames, gt_frames)] with the reference's chunking.
+    deblur (test_deblur_small.py:111-120): k_len = (n-4)//one_len, tail dropped.
+    denoise (test_denoise_small.py:113-131): one_len = n-4 (halved if > 100), the last chunk takes the remainder."""
+    units = []
+    for v in sorted(videos):
+        ins, gts = videos[v]
+        n = len(ins)
+        if task == "deblur":
+            L = one_len
+            for kk in range((n - 4) // L):
+                units.append((v, kk, ins[kk * L:kk * L + L + 4], gts[kk * L + 2:kk * L + 2 + L]))
+        else:
+            L = n - 4
+            if L > 100:
+                L //= 2
+            k_len, k_res = (n - 4) // L, (n - 4) % L
+            for kk in range(k_len):
+                add = k_res if kk == k_len - 1 else 0
+                units.append((v, kk, ins[kk * L:kk * L + L + add + 4], ins[kk * L + 2:kk * L + L + add + 2]))
+    return units
+
+
+def to_tensor(frames):
+    """uint8 HWC list -> (1,T,3,H,W) float32 in [0,1]; cropped to multiples of 4 (test_deblur_small.py:124-128,191-200)."""
+    frames = [np.asarray(_imread(f) if isinstance(f, str) else f) for f in frames]
+    h, w = frames[0].shape[:2]
+    h, w = h - h % 4, w - w % 4
+    frames = [f[:h, :w] for f in frames]
+    t = torch.from_numpy(np.ascontiguousarray(np.stack(frames))).permute(0, 3, 1, 2).float().div_(255.0)
+    return t.unsqueeze(0), frames
+
+
+def gather_records(records, device):
+    """all_gather of (video_idx, frame_idx, psnr, ssim) rows across ranks -> full list on every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return records
+    world = dist.get_world_size()
+    n = torch.tensor([len(records)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    m = max(int(c.item()) for c in counts)
+    buf = torch.zeros(max(m, 1), 4, dtype=torch.float64, device=device)
+    if records:
+        buf[:len(records)] = torch.tensor(records, dtype=torch.float64, device=device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    out = []
+    for c, b in zip(counts, bufs):
+        out += [tuple(r) for r in b[:int(c.item())].cpu().tolist()]
+    return out
+
+
+def summarize(records, names, task, log):
+    per = {}
+    for vi, fi, p, s in sorted(records):
+        per.setdefault(int(vi), []).append((p, s))
+    sp = ss = n = 0.0
+    sp2 = ss2 = 0.0
+    for vi in sorted(per):
+        ps = [x[0] for x in per[vi]]
+        sm = [x[1] for x in per[vi]]
+        log("# Video:{} AVG-PSNR={:.5}, AVG-SSIM={:.4}".format(names[vi], sum(ps) / len(ps), sum(sm) / len(sm)))
+        sp += sum(ps); ss += sum(sm); n += len(ps)
+        sp2 += sum(ps) / len(ps); ss2 += sum(sm) / len(sm)
+    if n:
+        log("# Total AVG-PSNR={:.5}, AVG-SSIM={:.4}".format(sp / n, ss / n))
+        if task == "denoise":                                  # test_denoise_small.py:223-224 also prints the mean of means
+            log("# Total AVG-PSNR={:.5}, AVG-SSIM={:.4}".format(sp2 / len(per), ss2 / len(per)))
+    return (sp / n, ss / n) if n else (float("nan"), float("nan"))
+
+
+def run(net_cls, task, args):
+    """Shared body of the four entry scripts.  ``net_cls`` is the arch's GShiftNet."""
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    use_cuda = torch.cuda.is_available()
+    device = torch.device("cuda", local) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if use_cuda else "gloo")
+    os.makedirs(args.result_path, exist_ok=True)
+    log = TraverseLogger(args.result_path, "inference_log_{}.txt".format(time.strftime("%Y-%m-%d %H:%M:%S")), rank == 0)
+    log.write_log("Inference - {} (shiftnet_b200, {} rank(s))".format(time.strftime("%Y-%m-%d %H:%M:%S"), world))
+
+    net = net_cls(future_frames=2, past_frames=2)
+    if args.model_path and os.path.exists(args.model_path):
+        net.load_state_dict(torch.load(args.model_path, map_location="cpu")["params"])
+        log.write_log("Loading model from {}".format(args.model_path))
+    else:
+        importlib_synth = __import__("importlib").import_module("shift-net_b200.host.synth")
+        importlib_synth.randomize_(net, 1234)
+        log.write_log("No checkpoint at {!r}: using the seeded synthetic checkpoint".format(args.model_path))
+    net = net.half().to(device).eval()
+
+    if args.synthetic:
+        videos = synthetic_videos(args.synthetic, args.synthetic_frames, args.synthetic_h, args.synthetic_w)
+    else:
+        in_dir = os.path.join(args.data_path, "blur") if task == "deblur" else args.data_path
+        gt_dir = os.path.join(args.data_path, "gt") if task == "deblur" else args.data_path
+        videos = {v: (sorted(glob.glob(os.path.join(in_dir, v, "*"))), sorted(glob.glob(os.path.join(gt_dir, v, "*"))))
+                  for v in sorted(os.listdir(in_dir))}
+    names = sorted(videos)
+    units = plan_units(videos, task, getattr(args, "one_len", 0))
+    records = []
+    with torch.no_grad():
+        for ui in range(rank, len(units), world):             # clip sharding: unit i -> rank i % world
+            v, kk, in_seq, gt_seq = units[ui]
+            t0 = time.time()
+            x, _ = to_tensor(in_seq)
+            _, gts = to_tensor(gt_seq)
+            T = x.shape[1]
+            if task == "deblur":
+                out = net(x.to(device).half()).float()
+            else:
+                sigma = args.sigma / 255.0
+                g = torch.Generator().manual_seed(1000 * names.index(v) + kk)
+                x = (x + sigma * torch.randn(x.shape, generator=g)).to(device).half()
+                B, N, _, H, W = x.shape
+                std = torch.full((1, 1, 1, 1, 1), sigma, device=device, dtype=torch.float16)
+                ph, pw = 32 - (H // 2 % 16), 32 - (W // 2 % 16)   # 2x2 overlapped tiling, test_denoise_small.py:153-173
+                out = torch.zeros(N - 4, 3, H, W, device=device)
+                hh, ww = H // 2 + ph, W // 2 + pw
+                nm = std.expand(B, N, 1, hh, ww)
+                o = net(x[..., 0:hh, 0:ww].contiguous(), nm).float(); out[..., 0:H // 2, 0:W // 2] = o[..., 0:-ph, 0:-pw]
+                o = net(x[..., 0:hh, W // 2 - pw:].contiguous(), nm).float(); out[..., 0:H // 2, W // 2:] = o[..., 0:-ph, pw:]
+                o = net(x[..., H // 2 - ph:, 0:ww].contiguous(), nm).float(); out[..., H // 2:, 0:W // 2] = o[..., ph:, 0:-pw]
+                o = net(x[..., H // 2 - ph:, W // 2 - pw:].contiguous(), nm).float(); out[..., H // 2:, W // 2:] = o[..., ph:, pw:]
+            t1 = time.time()
+            imgs = (out.clamp(0, 1.0) * 255).permute(0, 2, 3, 1).cpu().numpy()
+            base = kk * (T - 4)
+            for e in range(imgs.shape[0]):
+                p, s = psnr_255(imgs[e], gts[e]), ssim_calculate(imgs[e], gts[e])
+                records.append((names.index(v), base + e, p, s))
+                if args.save_image:
+                    import cv2
+                    os.makedirs(os.path.join(args.result_path, v), exist_ok=True)
+                    cv2.imwrite(os.path.join(args.result_path, v, "%03d.png" % (base + e)), imgs[e][..., ::-1])
+            print("> [rank {}] {}-{} PSNR={:.5}, SSIM={:.4} forward_time:{:.3}s, total_time:{:.3}s".format(
+                rank, v, kk, p, s, t1 - t0, time.time() - t0), flush=True)
+    records = gather_records(records, device)
+    res = summarize(records, names, task, log.write_log)
+    if world > 1 and dist.is_initialized():
+        dist.barrier()
+    return res, records
+
+
+def add_common_args(parser):
+    parser.add_argument("--save_image", action="store_true", default=False, help="save image if true")
+    parser.add_argument("--border", action="store_true", help="restore border images of video if true")
+    parser.add_argument("--default_data", type=str, default=".")
+    parser.add_argument("--data_path", type=str, default=None)
+    parser.add_argument("--model_path", type=str, default=None)
+    parser.add_argument("--result_path", type=str, default=None)
+    parser.add_argument("--synthetic", type=int, default=0, help="number of synthetic videos (no dataset needed)")
+    parser.add_argument("--synthetic_frames", type=int, default=12)
+    parser.add_argument("--synthetic_h", type=int, default=64)
+    parser.add_argument("--synthetic_w", type=int, default=96)
+    return parser

@@ -264,3 +264,15 @@ def test_full_size_cyclic_frame_equivariance(env):
     assert torch.equal(b[1:], a[:-1])
     # and the run is deterministic
     assert torch.equal(net(x), a)
+
+
+def test_inference_entry_point_synthetic(tmp_path):
+    """The reference's CLI (inference/test_deblur_small.py) end to end on generated videos, single rank."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(gio.ROOT, "inference", "test_deblur_small.py"), "--synthetic", "2",
+                        "--one_len", "4", "--synthetic_frames", "12", "--result_path", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("# ")]
+    assert len(lines) == 3 and lines[-1].startswith("# Total AVG-PSNR="), r.stdout[-2000:]
+    assert any(f.startswith("inference_log_") for f in os.listdir(tmp_path))
