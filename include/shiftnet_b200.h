@@ -117,10 +117,24 @@ typedef struct {
   float *chan_partial;  /* out: [T][gsn_cab_tiles][C] fp32 per-tile channel sums of z */
   int debug_stage;      /* 0 = normal; >0 dumps an intermediate smem stage to debug_out (tests only) */
   void *debug_out;
+  int mid_ca;           /* denoise variants (gshift_denoise2.py:194,227: a CALayer2 sits between the first gate and the
+                           RepConv).  A per-channel scale commutes with the depthwise RepConv, so with mid_ca=1 pass A
+                           stops after the RepConv: ``z`` receives u = RepConv(gate) (C ch) and ``chan_partial`` the
+                           per-tile sums of the gated tensor; gsn_cab_fold_mid + gsn_cab_pass_a2 finish the block. */
 } GsnCabPassA;
 
 int gsn_cab_tiles(int mode, int H, int W);
 int gsn_cab_pass_a(const GsnCabPassA *d, void *stream);
+
+/* mid fold (denoise): w2eff[t] = W2 diag(s1_t) as fp16 [T][C/8][2C][8], s1 from the mid CALayer2 on mean(gated).
+ * w_du0 [cr][C], w_du2 [C][cr], w2 [2C][C] (fp32). */
+int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,
+                     const float *w2, int C, int T, void *w2eff, void *stream);
+
+/* pass A2 (denoise): z = a * sigmoid(b), [a|b] = w2eff_t . u  (1x1 C->2C + SimpleGate2, gshift_denoise2.py:196-197),
+ * plus per-tile channel sums of z: chan_partial [T][gsn_cab_tiles_linear(H*W)][C]. */
+int gsn_cab_tiles_linear(long long hw);
+int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C, void *stream);
 
 /* fold: weff[t] = diag(beta) W3 diag(s_t) as fp16 [T][C/8][C][8] (k-chunk planar), s_t from CALayer2
  * (d2:72-89,238-239,257).  w_du0 [cr][C], w_du2 [C][cr], w3 [C][C], beta [C], bias3 [C] or NULL (fp32).

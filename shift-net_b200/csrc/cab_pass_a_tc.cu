@@ -171,7 +171,7 @@ struct TcCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int C, bool SHIFT>
+template <int C, bool SHIFT, bool MIDCA>
 __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnCabPassA d, const ShiftTable tab) {
   using K = TcCfg<C, SHIFT>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -576,6 +576,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A2 + (i / K::M3) * K::P3 + (i % K::M3) * 16);
   }
 
+  if (MIDCA) {
+    // denoise variants: stop here.  u = RepConv(gate) goes to HBM, the mid CALayer2 needs the frame mean of the gated
+    // tensor (sums over this tile's 16x16 centre of GATED); the scale it produces is folded into W2 by cab_fold_mid.
+    __half *ug = reinterpret_cast<__half *>(d.z) + (size_t)t * frame;
+    for (int i = tid; i < K::M3 * K::KC2; i += kTcThreads) {
+      const int ch = i % K::KC2, p = i / K::KC2;
+      const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
+      if (gy < d.H && gx < d.W)
+        *reinterpret_cast<uint4 *>(ug + ((size_t)gy * d.W + gx) * C + ch * 8) = *reinterpret_cast<const uint4 *>(smem + K::S_A2 + ch * K::P3 + p * 16);
+    }
+    float *red = reinterpret_cast<float *>(smem + K::S_X + K::X_RED);
+    for (int u = warp; u < K::KC2 * 2; u += kTcThreads / 32) {
+      const int ch = u % K::KC2, hf = u / K::KC2;
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      for (int p = hf * (K::M3 / 2) + lane; p < (hf + 1) * (K::M3 / 2); p += 32) {
+        const int oy = p / K::TW, ox = p % K::TW;
+        if (y0 + oy < d.H && x0 + ox < d.W) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_GT + ch * K::P2 + ((oy + 2) * K::R2W + ox + 2) * 16), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[hf * C + ch * 8 + i] = s[i];
+      }
+    }
+    __syncthreads();
+    if (tid < C) {
+      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = red[tid] + red[C + tid];
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512));
+    return;
+  }
+
   // ---- P6: GEMM2 on the tensor core: (256 x C) . W2^T -> TMEM columns [0, 2*N) -------------------------------------
   if (tid == 0) {
     tc_fence_after();
@@ -662,25 +706,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
 }
 
-template <int C, bool SHIFT>
+template <int C, bool SHIFT, bool MIDCA>
 static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st) {
   using K = TcCfg<C, SHIFT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT, MIDCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     attr_set = true;
   }
   static const ShiftTable tab = make_shift_table(C);
   dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + K::TH - 1) / K::TH, d.T);
-  cab_pass_a_tc_kernel<C, SHIFT><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
+  cab_pass_a_tc_kernel<C, SHIFT, MIDCA><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
   count_launch();
   return check_launch("cab_pass_a_tc");
 }
 
 int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st) {
   if (d.C == 64) {
-    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false>(d, st);
-    return launch_pass_a_tc<64, true>(d, st);
+    if (d.mid_ca) {
+      if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, true>(d, st);
+      return launch_pass_a_tc<64, true, true>(d, st);
+    }
+    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, false>(d, st);
+    return launch_pass_a_tc<64, true, false>(d, st);
   }
   set_error("cab_pass_a: C=%d unsupported (64)", d.C);
   return GSN_E_UNSUPPORTED;

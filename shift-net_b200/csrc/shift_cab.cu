@@ -476,6 +476,134 @@ __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// denoise variants: mid CALayer2 folded into W2, and the pointwise tail of pass A as its own kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cab_fold_mid_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
+                                                           const float *__restrict__ w_du0, const float *__restrict__ w_du2,
+                                                           int cr, const float *__restrict__ w2, int C,
+                                                           __half *__restrict__ w2eff) {
+  __shared__ float mean[128], hid[128], sc[128], part[256];
+  const int t = blockIdx.x, tid = threadIdx.x;
+  {
+    const int nparts = 256 / C, ch = tid % C, pi = tid / C;
+    float a = 0.f;
+    if (pi < nparts) {
+      const float *p = partial + (size_t)t * ntiles * C + ch;
+      for (int i = pi; i < ntiles; i += nparts) a += p[(size_t)i * C];
+    }
+    part[tid] = a;
+    __syncthreads();
+    if (tid < C) {
+      float m = 0.f;
+      for (int q = 0; q < nparts; ++q) m += part[q * C + tid];
+      mean[tid] = m * inv_hw;
+    }
+  }
+  __syncthreads();
+  if (tid < cr) {
+    float a = 0.f;
+    for (int i = 0; i < C; ++i) a += w_du0[tid * C + i] * mean[i];
+    hid[tid] = a > 0.f ? a : 0.f;
+  }
+  __syncthreads();
+  if (tid < C) {
+    float a = 0.f;
+    for (int i = 0; i < cr; ++i) a += w_du2[tid * cr + i] * hid[i];
+    sc[tid] = 1.f / (1.f + expf(-a));
+  }
+  __syncthreads();
+  __half *wt = w2eff + (size_t)t * 2 * C * C;
+  for (int i = tid; i < 2 * C * C; i += 256) {
+    const int n = i / C, k = i - n * C;
+    wt[((k >> 3) * 2 * C + n) * 8 + (k & 7)] = __float2half_rn(w2[n * C + k] * sc[k]);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) cab_pass_a2_kernel(const __half *__restrict__ u, const __half *__restrict__ w2eff,
+                                                          __half *__restrict__ z, float *__restrict__ chan_partial,
+                                                          long long hw) {
+  constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, N = 2 * C, NTH = C / 8;
+  __shared__ __align__(128) unsigned char su[KC * PZ];
+  __shared__ __align__(128) unsigned char sw[KC * N * 16];
+  __shared__ float red[8 * C];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * MP;
+  const size_t frame = (size_t)hw * C;
+  {
+    const unsigned char *wg = reinterpret_cast<const unsigned char *>(w2eff) + (size_t)t * N * C * 2;
+    for (int i = tid; i < KC * N; i += 256) cp_async16(sw + i * 16, wg + i * 16, true);
+    const __half *ug = u + (size_t)t * frame;
+    for (int i = tid; i < MP * KC; i += 256) {
+      const int ch = i % KC, p = i / KC;
+      const bool valid = p0 + p < hw;
+      cp_async16(su + ch * PZ + p * 16, ug + (valid ? (size_t)(p0 + p) * C + ch * 8 : 0), valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+  const int g = lane >> 2, tig = lane & 3;
+  float acc[2 * NTH][4];
+#pragma unroll
+  for (int n = 0; n < 2 * NTH; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+  const uint32_t u_s = smem_u32(su), w_s = smem_u32(sw);
+#pragma unroll
+  for (int k = 0; k < KC / 2; ++k) {
+    uint32_t a[4];
+    ldmatrix_x4(a[0], a[1], a[2], a[3], u_s + (2 * k + (lane >> 4)) * PZ + (warp * 16 + (lane & 15)) * 16);
+#pragma unroll
+    for (int np = 0; np < NTH; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4(b[0], b[1], b[2], b[3], w_s + ((2 * k + ((lane >> 3) & 1)) * N + np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * 16);
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+  __syncwarp();
+  float csum[NTH][2];
+#pragma unroll
+  for (int n = 0; n < NTH; ++n) {
+    csum[n][0] = csum[n][1] = 0.f;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int p = warp * 16 + g + hrow * 8;
+      const float z0 = acc[n][hrow * 2] * sigmoidf_fast(acc[n + NTH][hrow * 2]);
+      const float z1 = acc[n][hrow * 2 + 1] * sigmoidf_fast(acc[n + NTH][hrow * 2 + 1]);
+      if (p0 + p < hw) { csum[n][0] += z0; csum[n][1] += z1; }
+      // each warp only touches the rows of su it has finished reading: reuse them as the z staging tile
+      *reinterpret_cast<uint32_t *>(su + n * PZ + p * 16 + tig * 4) = pack_half2(z0, z1);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NTH; ++n)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = csum[n][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0) red[warp * C + n * 8 + tig * 2 + j] = v;
+    }
+  __syncthreads();
+  __half *zg = z + (size_t)t * frame;
+  for (int i = tid; i < MP * KC; i += 256) {
+    const int ch = i % KC, p = i / KC;
+    if (p0 + p < hw)
+      *reinterpret_cast<uint4 *>(zg + (size_t)(p0 + p) * C + ch * 8) = *reinterpret_cast<const uint4 *>(su + ch * PZ + p * 16);
+  }
+  if (tid < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w * C + tid];
+    chan_partial[((size_t)t * gridDim.x + blockIdx.x) * C + tid] = s;
+  }
+}
+
 template <int C, bool SHIFT, int TH>
 static int launch_pass_a(const GsnCabPassA &d, cudaStream_t st) {
   using K = PassACfg<C, SHIFT, TH>;
@@ -517,13 +645,44 @@ extern "C" int gsn_cab_pass_a(const GsnCabPassA *dp, void *stream) {
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_a: mode=%d", d.mode);
   GSN_REQUIRE(d.debug_stage == 0 || d.debug_out, "cab_pass_a: debug_stage without debug_out");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!use_legacy_pass_a()) return cab_pass_a_tc_dispatch(d, st);
+  if (!use_legacy_pass_a() || d.mid_ca) return cab_pass_a_tc_dispatch(d, st);
   if (d.C == 64) {
     if (d.mode == GSN_MODE_CAB1) return launch_pass_a<64, false, kTileH_Cab1>(d, st);
     return launch_pass_a<64, true, kTileH_Cab2>(d, st);
   }
   set_error("cab_pass_a: C=%d unsupported (64)", d.C);
   return GSN_E_UNSUPPORTED;
+}
+
+extern "C" int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,
+                                const float *w2, int C, int T, void *w2eff, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(partial && w_du0 && w_du2 && w2 && w2eff, "cab_fold_mid: null pointer");
+  GSN_REQUIRE(C > 0 && C <= 128 && C % 8 == 0 && cr > 0 && cr <= 128 && ntiles > 0 && T > 0, "cab_fold_mid: bad sizes C=%d cr=%d", C, cr);
+  cab_fold_mid_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, ntiles, inv_hw, w_du0, w_du2, cr, w2, C,
+                                                                              reinterpret_cast<__half *>(w2eff));
+  count_launch();
+  return check_launch("cab_fold_mid");
+}
+
+extern "C" int gsn_cab_tiles_linear(long long hw) { return (int)((hw + 127) / 128); }
+
+extern "C" int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C,
+                               void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(u && w2eff && z && chan_partial, "cab_pass_a2: null pointer");
+  GSN_REQUIRE(T > 0 && H > 0 && W > 0, "cab_pass_a2: empty shape");
+  const long long hw = (long long)H * W;
+  dim3 grid((unsigned)((hw + 127) / 128), T);
+  if (C == 64) {
+    cab_pass_a2_kernel<64><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff), reinterpret_cast<__half *>(z), chan_partial, hw);
+  } else {
+    set_error("cab_pass_a2: C=%d unsupported (64)", C);
+    return GSN_E_UNSUPPORTED;
+  }
+  count_launch();
+  return check_launch("cab_pass_a2");
 }
 
 extern "C" int gsn_cab_fold(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,

@@ -20,10 +20,10 @@ class Engine:
     def __init__(self, spec, state_dict, device):
         if torch.device(device).type != "cuda":
             raise RuntimeError("shiftnet_b200: the engine runs on CUDA only (no CPU fallback)")
-        if spec.plus or spec.denoise:
+        if spec.plus:
             raise NotImplementedError(
-                f"shiftnet_b200: arch {spec.name} is not implemented in the CUDA path yet (Ours+: C=80 / grouped RepConv; "
-                "denoise: the extra mid-block CALayer2 needs a third pass) -- only gshift_deblur2 runs so far")
+                f"shiftnet_b200: arch {spec.name} (Ours+: C=80, grouped RepConv, 3-level stage 1) is not implemented in "
+                "the CUDA path yet -- gshift_deblur2 and gshift_denoise2 run")
         self.spec = spec
         self.dev = torch.device(device)
         self.lib = L.load()
@@ -186,12 +186,26 @@ class Engine:
         a = L.CabPassA()
         a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), partial.data_ptr()
+        a.mid_ca = 1 if self.spec.denoise else 0
         dbg = None
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
             a.debug_stage, a.debug_out = debug_stage, dbg.data_ptr()
         with self._timed("cab_pass_a_shift" if shift else "cab_pass_a", T * H * W):
             L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
+        if self.spec.denoise:
+            # z holds u = RepConv(gate); finish the block: mid CALayer2 folded into W2, then 1x1 + sigmoid gate
+            u = z
+            w2eff = self._new(T, 2 * Cc * Cc)
+            L.check(self.lib.gsn_cab_fold_mid(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["mid_du0"].data_ptr(),
+                                              fw["mid_du2"].data_ptr(), fw["mid_du0"].shape[0], fw["w2"].data_ptr(), Cc, T,
+                                              w2eff.data_ptr(), self._stream()), "cab_fold_mid")
+            ntiles = self.lib.gsn_cab_tiles_linear(H * W)
+            partial = self._new(T, ntiles, Cc, dtype=torch.float32)
+            z = self._new(T, H, W, Cc)
+            with self._timed("cab_pass_a2", T * H * W):
+                L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2eff.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc,
+                                                 self._stream()), "cab_pass_a2")
         weff = self._new(T, Cc * Cc)
         beff = self._new(T, Cc, dtype=torch.float32)
         L.check(self.lib.gsn_cab_fold(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["du0"].data_ptr(), fw["du2"].data_ptr(),

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libshiftnet_b200.so")
 EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
-    "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b",
+    "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
 ]
 
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
@@ -34,7 +34,7 @@ class CabPassA(C.Structure):
     _fields_ = [
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("mode", C.c_int), ("circular", C.c_int),
         ("x", C.c_void_p), ("wblob", C.c_void_p), ("z", C.c_void_p), ("chan_partial", C.c_void_p),
-        ("debug_stage", C.c_int), ("debug_out", C.c_void_p),
+        ("debug_stage", C.c_int), ("debug_out", C.c_void_p), ("mid_ca", C.c_int),
     ]
 
 
@@ -74,6 +74,9 @@ def load():
     lib.gsn_cab_pass_a.argtypes = [C.POINTER(CabPassA), vp]
     lib.gsn_cab_fold.argtypes = [vp, i, f, vp, vp, i, vp, vp, vp, i, i, vp, vp, vp]
     lib.gsn_cab_pass_b.argtypes = [C.POINTER(CabPassB), vp]
+    lib.gsn_cab_fold_mid.argtypes = [vp, i, f, vp, vp, i, vp, i, i, vp, vp]
+    lib.gsn_cab_tiles_linear.argtypes = [ll]
+    lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     for n in EXPORTS:
         fn = getattr(lib, n)
         if fn.restype is C.c_int and n not in ("gsn_version", "gsn_conv_tiles", "gsn_cab_tiles"):

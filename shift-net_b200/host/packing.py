@@ -102,4 +102,8 @@ def pack_cab_fold(sd, p, body_off=0):
         beta=sd[p + ".beta"].float().reshape(-1).contiguous(),
         bias3=sd[last + ".bias"].float().contiguous() if (last + ".bias") in sd else None,
     )
+    if k:   # denoise: the mid CALayer2 (body.3) is folded into the second 1x1 (body.5) per frame
+        d["mid_du0"] = sd[p + ".body.3.conv_du.0.weight"].float().flatten(1).contiguous()
+        d["mid_du2"] = sd[p + ".body.3.conv_du.2.weight"].float().flatten(1).contiguous()
+        d["w2"] = sd[p + f".body.{4 + k}.weight"].float().flatten(1).contiguous()
     return d

@@ -47,11 +47,23 @@ def check(a, ref, tol, what):
     assert r < tol, (what, r, m)
 
 
+CUDA_ARCHS = ["gshift_deblur2", "gshift_denoise2"]       # archs whose CUDA path exists (Ours+ raises NotImplementedError)
+
+
+def _make_env(arch):
+    sd, spec = gio.synthetic_checkpoint(arch)
+    eng = gio.pkg("host.engine").Engine(spec, {k: v.to(DEV) for k, v in sd.items()}, DEV)
+    return sd, spec, eng, gio.load_golden(arch)
+
+
 @pytest.fixture(scope="module")
 def env():
-    sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
-    eng = gio.pkg("host.engine").Engine(spec, {k: v.to(DEV) for k, v in sd.items()}, DEV)
-    return sd, spec, eng, gio.load_golden("gshift_deblur2")
+    return _make_env("gshift_deblur2")
+
+
+@pytest.fixture(scope="module", params=CUDA_ARCHS)
+def aenv(request):
+    return _make_env(request.param)
 
 
 # ------------------------------------------------------------------------------------------------ dense conv
@@ -142,8 +154,8 @@ def test_upsample_add(env):
 
 
 # ------------------------------------------------------------------------------------------------ blocks
-def test_cab(env):
-    sd, spec, eng, gold = env
+def test_cab(aenv):
+    sd, spec, eng, gold = aenv
     x = gio.module_input("cab", spec)
     out = from_nhwc(eng.cab("feat_extract.1", to_nhwc(x), spec.n0), spec.n0)
     check(out, O.cab(sd, "feat_extract.1", x), 3e-3, "cab vs oracle")
@@ -152,8 +164,8 @@ def test_cab(env):
 
 @pytest.mark.parametrize("which", ["cab2_fwd", "cab2_rev", "cab1"])
 @pytest.mark.parametrize("circular", [True, False])
-def test_gated_cab(env, which, circular):
-    sd, spec, eng, gold = env
+def test_gated_cab(aenv, which, circular):
+    sd, spec, eng, gold = aenv
     L = gio.pkg("host.lib")
     x = gio.module_input("shift", spec)
     blk = "stage1.decoder_level1"
@@ -161,15 +173,15 @@ def test_gated_cab(env, which, circular):
     eng2.sd = eng.sd
     if which == "cab1":
         p, mode = blk + ".encoder_level1.1", L.MODE_CAB1
-        ref = O.cab1(sd, p, x, False)
+        ref = O.cab1(sd, p, x, spec.denoise)
     else:
         rev = which == "cab2_rev"
         p = blk + (".encoder_level1_1.0" if rev else ".encoder_level1.0")
         mode = L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD
-        ref = O.cab2(sd, p, O.channel_shift(x, rev, circular), spec.c1, False)
+        ref = O.cab2(sd, p, O.channel_shift(x, rev, circular), spec.c1, spec.denoise)
     out = from_nhwc(eng2.gated_cab(p, to_nhwc(x), mode), spec.c1)
-    check(out, ref, 3e-3, f"{which} circular={circular} vs oracle")
-    if circular:
+    check(out, ref, 3e-3, f"{spec.name} {which} circular={circular} vs oracle")
+    if circular == spec.circular:
         check(out, torch.from_numpy(gold[which]), 3e-3, f"{which} vs reference golden")
 
 
@@ -191,31 +203,32 @@ def test_gated_cab_ragged_sizes(env):
         check(out, ref, 3e-3, f"cab1 T={T} {H}x{W}")
 
 
-def test_shift_block(env):
-    sd, spec, eng, gold = env
+def test_shift_block(aenv):
+    sd, spec, eng, gold = aenv
     x = gio.module_input("shift", spec)
     out = from_nhwc(eng.shift_block("stage1.decoder_level1", to_nhwc(x)), spec.c1)
     check(out, O.shift_block(sd, "stage1.decoder_level1", x, O.ARCHS[spec.name]), 5e-3, "shift block vs oracle")
     check(out, torch.from_numpy(gold["block"]), 5e-3, "shift block vs reference golden")
 
 
-def test_tfr_unet(env):
-    sd, spec, eng, gold = env
+def test_tfr_unet(aenv):
+    sd, spec, eng, gold = aenv
     x = gio.module_input("tfr", spec)
     out = from_nhwc(eng.tfr_unet("orb1", to_nhwc(x)), spec.n0)
     check(out, O.tfr_unet(sd, "orb1", x, O.ARCHS[spec.name]), 5e-3, "TFR_UNet vs oracle")
     check(out, torch.from_numpy(gold["tfr"]), 5e-3, "TFR_UNet vs reference golden")
 
 
-def test_stage1(env):
-    sd, spec, eng, gold = env
+def test_stage1(aenv):
+    sd, spec, eng, gold = aenv
     x = gio.module_input("stage1", spec)
     out = from_nhwc(eng.stage1("stage1", to_nhwc(x)), spec.n0)
     check(out, torch.from_numpy(gold["stage1"]), 1e-2, "stage1 (Encoder2) vs reference golden")
 
 
-def _net(sd, dtype=torch.float16):
-    from basicsr.models.archs.gshift_deblur2 import GShiftNet
+def _net(sd, dtype=torch.float16, arch="gshift_deblur2"):
+    import importlib
+    GShiftNet = importlib.import_module("basicsr.models.archs." + arch).GShiftNet
     net = GShiftNet(future_frames=2, past_frames=2)
     net.load_state_dict(sd)
     net = net.to(DEV).eval()
@@ -223,15 +236,16 @@ def _net(sd, dtype=torch.float16):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
-def test_full_forward_golden(env, dtype):
-    """The drop-in call of inference/test_deblur_small.py:84-89,134 on the golden clip."""
-    sd, spec, _, gold = env
-    x, _ = gio.clip_input(spec)
-    out = _net(sd, dtype)(x.to(DEV, dtype))
+def test_full_forward_golden(aenv, dtype):
+    """The drop-in call of inference/test_deblur_small.py:84-89,134 (test_denoise_small.py:83-88,162) on the golden clip."""
+    sd, spec, _, gold = aenv
+    x, nm = gio.clip_input(spec)
+    net = _net(sd, dtype, spec.name)
+    out = net(x.to(DEV, dtype), nm.to(DEV, dtype)) if spec.denoise else net(x.to(DEV, dtype))
     assert out.dtype == dtype and tuple(out.shape) == (2, 3, 32, 40)
     ref = torch.from_numpy(gold["full"])
     p = O.psnr(out.float().cpu(), ref)
-    print(f"[parity] full forward {dtype}: PSNR vs reference fp32 = {p:.2f} dB")
+    print(f"[parity] {spec.name} full forward {dtype}: PSNR vs reference fp32 = {p:.2f} dB")
     assert p >= 50.0
 
 
@@ -264,6 +278,23 @@ def test_full_size_cyclic_frame_equivariance(env):
     assert torch.equal(b[1:], a[:-1])
     # and the run is deterministic
     assert torch.equal(net(x), a)
+
+
+def test_ours_plus_fails_loudly():
+    """Ours+ has no CUDA path yet: it must raise, never fall back."""
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur1")
+    net = _net(sd, arch="gshift_deblur1")
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 6, 3, 32, 32, device=DEV, dtype=torch.float16))
+
+
+def test_denoise_entry_point_synthetic(tmp_path):
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(gio.ROOT, "inference", "test_denoise_small.py"), "--synthetic", "1",
+                        "--sigma", "30", "--synthetic_frames", "9", "--synthetic_h", "96", "--synthetic_w", "128",
+                        "--result_path", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sum(l.startswith("# Total AVG-PSNR=") for l in r.stdout.splitlines()) == 2, r.stdout[-2000:]
 
 
 def test_inference_entry_point_synthetic(tmp_path):
