@@ -13,9 +13,13 @@
 
 namespace gsn {
 
-template <int NT, int KS, int STRIDE>
-__global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const GsnConvDesc d, int pitch) {
+// CINP > 0: padded input width known at compile time (curated list of the layer shapes the nets use) -> the tap / k-step
+// loops unroll completely and every shared-memory address is an immediate.  CINP == 0: generic runtime fallback.
+template <int NT, int KS, int STRIDE, int CINP>
+__global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const GsnConvDesc d) {
   constexpr int IH = 15 * STRIDE + KS, IW = IH;   // compile-time tile geometry: no runtime integer divisions below
+  const int cin_p = CINP ? CINP : d.cin_p;
+  const int pitch = cin_p + 8;
   extern __shared__ __align__(16) unsigned char smem[];
   __half *tile = reinterpret_cast<__half *>(smem);
   float *red = reinterpret_cast<float *>(smem + (size_t)IH * IW * pitch * 2);
@@ -27,21 +31,38 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
 
   // ---- stage the input tile ---------------------------------------------------------------------
   {
-    const int chunks = d.cin_p >> 3;
-    const int c1 = d.src_c[0], c2 = d.src_c[0] + d.src_c[1];
-    for (int px = tid; px < IH * IW; px += 256) {
-      const int ly = px / IW, lx = px - ly * IW;
-      const int gy = iy0 + ly, gx = ix0 + lx;
-      const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
-      const size_t gpix = valid ? ((size_t)t * d.Hin + gy) * d.Win + gx : 0;
-      __half *dp = tile + (size_t)px * pitch;
-      for (int ch = 0; ch < chunks; ++ch) {
-        const int c = ch * 8;
-        int s = 0, cb = 0;
-        if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
-        else if (c >= c1 && d.n_src > 1) { s = 1; cb = c1; }
-        const __half *base = reinterpret_cast<const __half *>(d.src[s]);
-        cp_async16(dp + c, valid ? base + gpix * d.src_c[s] + (c - cb) : base, valid);
+    const int chunks = cin_p >> 3;
+    if (d.n_src == 1) {
+      const __half *base = reinterpret_cast<const __half *>(d.src[0]);
+      for (int px = tid; px < IH * IW; px += 256) {
+        const int ly = px / IW, lx = px - ly * IW;
+        const int gy = iy0 + ly, gx = ix0 + lx;
+        const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
+        const __half *sp = valid ? base + (((size_t)t * d.Hin + gy) * d.Win + gx) * cin_p : base;
+        __half *dp = tile + (size_t)px * pitch;
+#pragma unroll
+        for (int ch = 0; ch < (CINP ? CINP / 8 : 1); ++ch) {
+          if (CINP) cp_async16(dp + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+        }
+        if (!CINP)
+          for (int ch = 0; ch < chunks; ++ch) cp_async16(dp + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+      }
+    } else {
+      const int c1 = d.src_c[0], c2 = d.src_c[0] + d.src_c[1];
+      for (int px = tid; px < IH * IW; px += 256) {
+        const int ly = px / IW, lx = px - ly * IW;
+        const int gy = iy0 + ly, gx = ix0 + lx;
+        const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
+        const size_t gpix = valid ? ((size_t)t * d.Hin + gy) * d.Win + gx : 0;
+        __half *dp = tile + (size_t)px * pitch;
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int c = ch * 8;
+          int s = 0, cb = 0;
+          if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
+          else if (c >= c1) { s = 1; cb = c1; }
+          const __half *base = reinterpret_cast<const __half *>(d.src[s]);
+          cp_async16(dp + c, valid ? base + gpix * d.src_c[s] + (c - cb) : base, valid);
+        }
       }
     }
     cp_async_commit();
@@ -60,72 +81,102 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
 
   const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;  // output x within the M tile
   const int akof = (lane >> 4) * 8;                     // k half (0 / 8) this lane addresses
-  const int ksteps = d.cin_p >> 4;
-  const uint2 *wp = reinterpret_cast<const uint2 *>(d.wpack);
-  const uint32_t tile_s = smem_u32(tile);
+  const int ksteps = cin_p >> 4;
+  const uint2 *wp = reinterpret_cast<const uint2 *>(d.wpack) + lane;
+  // per-lane base address of the two M tiles (output rows 2*warp, 2*warp+1); taps / k-steps add constants
+  const uint32_t a_base0 = smem_u32(tile) + (uint32_t)((((2 * warp) * STRIDE * IW + arow * STRIDE) * pitch + akof) * 2);
+  const uint32_t a_row = (uint32_t)(STRIDE * IW * pitch * 2);
   constexpr int taps = KS * KS;
 
+  if (CINP) {
+    constexpr int KSTEPS = CINP ? CINP / 16 : 1;
+    constexpr int PITCH = CINP + 8;
+    // narrow layers: unroll a whole kernel row (addresses become immediates); wide layers: keep the loops rolled so the
+    // compiler does not hoist dozens of B-fragment loads into registers (spills)
 #pragma unroll 1
-  for (int tap = 0; tap < taps; ++tap) {
-    const int ky = tap / KS, kx = tap - ky * KS;
-    const int ix = arow * STRIDE + kx;
-    for (int k = 0; k < ksteps; ++k) {
-      uint32_t a[2][4];
+    for (int ky = 0; ky < KS; ++ky) {
+      const uint32_t rowoff = (uint32_t)(ky * IW * PITCH * 2);
+#pragma unroll(CINP <= 32 ? KS : 1)
+      for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll(CINP <= 32 ? KSTEPS : 1)
+        for (int k = 0; k < KSTEPS; ++k) {
+          const uint32_t off = rowoff + (uint32_t)((kx * PITCH + k * 16) * 2);
+          uint32_t a0[4], a1[4];
+          ldmatrix_x4(a0[0], a0[1], a0[2], a0[3], a_base0 + off);
+          ldmatrix_x4(a1[0], a1[1], a1[2], a1[3], a_base0 + a_row + off);
+          const uint2 *wk = wp + (size_t)(((ky * KS + kx) * KSTEPS + k) * NT) * 32;
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int iy = (2 * warp + m) * STRIDE + ky;
-        const uint32_t addr = tile_s + (uint32_t)(((iy * IW + ix) * pitch + k * 16 + akof) * 2);
-        ldmatrix_x4(a[m][0], a[m][1], a[m][2], a[m][3], addr);
+          for (int n = 0; n < NT; ++n) {
+            const uint2 b = __ldg(wk + n * 32);
+            mma16816(acc[0][n], a0, b.x, b.y);
+            mma16816(acc[1][n], a1, b.x, b.y);
+          }
+        }
       }
-      const uint2 *wk = wp + ((size_t)(tap * ksteps + k) * NT) * 32 + lane;
+    }
+  } else {
+#pragma unroll 1
+    for (int tap = 0; tap < taps; ++tap) {
+      const int ky = tap / KS, kx = tap - ky * KS;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint32_t off = (uint32_t)(((ky * IW + kx) * pitch + k * 16) * 2);
+        uint32_t a0[4], a1[4];
+        ldmatrix_x4(a0[0], a0[1], a0[2], a0[3], a_base0 + off);
+        ldmatrix_x4(a1[0], a1[1], a1[2], a1[3], a_base0 + a_row + off);
+        const uint2 *wk = wp + (size_t)((tap * ksteps + k) * NT) * 32;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const uint2 b = __ldg(wk + n * 32);
-        mma16816(acc[0][n], a[0], b.x, b.y);
-        mma16816(acc[1][n], a[1], b.x, b.y);
+        for (int n = 0; n < NT; ++n) {
+          const uint2 b = __ldg(wk + n * 32);
+          mma16816(acc[0][n], a0, b.x, b.y);
+          mma16816(acc[1][n], a1, b.x, b.y);
+        }
       }
     }
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------
   const int g = lane >> 2, tig = lane & 3;
-  float csum[NT][2];
+  float csum[NT][2], bia[NT][2];
 #pragma unroll
-  for (int n = 0; n < NT; ++n) csum[n][0] = csum[n][1] = 0.f;
-
+  for (int n = 0; n < NT; ++n) {
+    csum[n][0] = csum[n][1] = 0.f;
+    bia[n][0] = d.bias ? __ldg(d.bias + n * 8 + tig * 2) : 0.f;
+    bia[n][1] = d.bias ? __ldg(d.bias + n * 8 + tig * 2 + 1) : 0.f;
+  }
   __half *dst = reinterpret_cast<__half *>(d.dst);
   const __half *res = reinterpret_cast<const __half *>(d.residual);
+  const int cout_p = NT * 8;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int oy = oy0 + 2 * warp + m;
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int ox = ox0 + g + hrow * 8;
-      const bool ok = (oy < d.Hout) && (ox < d.Wout);
+      if (oy >= d.Hout || ox >= d.Wout) continue;
       const size_t opix = ((size_t)t * d.Hout + oy) * d.Wout + ox;
+      __half *dp = dst + opix * cout_p + tig * 2;
+      const __half *rp = res ? res + opix * cout_p + tig * 2 : nullptr;
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-        const int co = n * 8 + tig * 2;
-        float v0 = acc[m][n][hrow * 2 + 0], v1 = acc[m][n][hrow * 2 + 1];
-        if (d.bias) { v0 += __ldg(d.bias + co); v1 += __ldg(d.bias + co + 1); }
+        float v0 = acc[m][n][hrow * 2 + 0] + bia[n][0], v1 = acc[m][n][hrow * 2 + 1] + bia[n][1];
         if (d.has_prelu) {
           v0 = v0 > 0.f ? v0 : v0 * d.prelu_slope;
           v1 = v1 > 0.f ? v1 : v1 * d.prelu_slope;
         }
-        if (!ok) continue;
-        if (res) {
-          const float2 r = unpack_half2(*reinterpret_cast<const uint32_t *>(res + opix * d.cout_p + co));
+        if (rp) {
+          const float2 r = unpack_half2(*reinterpret_cast<const uint32_t *>(rp + n * 8));
           v0 += r.x; v1 += r.y;
         }
         csum[n][0] += v0; csum[n][1] += v1;
         if (!d.pixel_shuffle) {
-          *reinterpret_cast<uint32_t *>(dst + opix * d.cout_p + co) = pack_half2(v0, v1);
+          *reinterpret_cast<uint32_t *>(dp + n * 8) = pack_half2(v0, v1);
         } else {
           // F.pixel_shuffle(.,2): conv channel co = c*4 + i*2 + j -> dst[c, 2y+i, 2x+j]; co is even => j = 0 / 1
-          const int cd = d.cout_p >> 2, c = co >> 2, i = (co >> 1) & 1;
-          const size_t dp = (((size_t)t * 2 * d.Hout + 2 * oy + i) * (2 * d.Wout) + 2 * ox) * cd + c;
-          dst[dp] = __float2half_rn(v0);
-          dst[dp + cd] = __float2half_rn(v1);
+          const int co = n * 8 + tig * 2;
+          const int cd = cout_p >> 2, c = co >> 2, i = (co >> 1) & 1;
+          const size_t sp = (((size_t)t * 2 * d.Hout + 2 * oy + i) * (2 * d.Wout) + 2 * ox) * cd + c;
+          dst[sp] = __float2half_rn(v0);
+          dst[sp + cd] = __float2half_rn(v1);
         }
       }
     }
@@ -141,20 +192,20 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) red[warp * d.cout_p + n * 8 + tig * 2 + j] = v;
+        if (g == 0) red[warp * cout_p + n * 8 + tig * 2 + j] = v;
       }
     __syncthreads();
-    if (tid < d.cout_p) {
+    if (tid < cout_p) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * d.cout_p + tid];
+      for (int w = 0; w < 8; ++w) s += red[w * cout_p + tid];
       const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * d.cout_p + tid] = s;
+      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * cout_p + tid] = s;
     }
   }
 }
 
-template <int NT, int KS, int STRIDE>
+template <int NT, int KS, int STRIDE, int CINP>
 static int launch_conv(const GsnConvDesc &d, cudaStream_t st) {
   constexpr int IH = 15 * STRIDE + KS, IW = IH;
   const int pitch = d.cin_p + 8;
@@ -162,21 +213,30 @@ static int launch_conv(const GsnConvDesc &d, cudaStream_t st) {
   if (smem > 227 * 1024) { set_error("conv_mma: tile needs %zu B smem", smem); return GSN_E_UNSUPPORTED; }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_mma_kernel<NT, KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<NT, KS, STRIDE, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   dim3 grid((d.Wout + 15) / 16, (d.Hout + 15) / 16, d.T);
-  conv_mma_kernel<NT, KS, STRIDE><<<grid, 256, smem, st>>>(d, pitch);
+  conv_mma_kernel<NT, KS, STRIDE, CINP><<<grid, 256, smem, st>>>(d);
   count_launch();
   return check_launch("conv_mma");
 }
 
 template <int NT>
 static int launch_conv_nt(const GsnConvDesc &d, cudaStream_t st) {
-  if (d.ks == 3 && d.stride == 1) return launch_conv<NT, 3, 1>(d, st);
-  if (d.ks == 3 && d.stride == 2) return launch_conv<NT, 3, 2>(d, st);
-  if (d.ks == 1 && d.stride == 1) return launch_conv<NT, 1, 1>(d, st);
-  if (d.ks == 2 && d.stride == 2) return launch_conv<NT, 2, 2>(d, st);
+  const int key = d.cin_p * 100 + d.ks * 10 + d.stride;
+  // specialised (fully unrolled) instances for the layer shapes of the four nets
+#define GSN_CONV_CASE(CIN, K, S) if (key == CIN * 100 + K * 10 + S) return launch_conv<NT, K, S, CIN>(d, st);
+  if constexpr (NT == 2) { GSN_CONV_CASE(16, 3, 1) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 1) }
+  if constexpr (NT == 4) { GSN_CONV_CASE(32, 3, 1) GSN_CONV_CASE(16, 3, 2) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 1, 1) GSN_CONV_CASE(96, 3, 1) GSN_CONV_CASE(64, 3, 1) }
+  if constexpr (NT == 6) { GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(48, 3, 2) GSN_CONV_CASE(48, 1, 1) }
+  if constexpr (NT == 8) { GSN_CONV_CASE(64, 3, 1) GSN_CONV_CASE(64, 3, 2) GSN_CONV_CASE(64, 1, 1) GSN_CONV_CASE(16, 2, 2) }
+  if constexpr (NT == 10) { GSN_CONV_CASE(80, 3, 1) GSN_CONV_CASE(80, 3, 2) GSN_CONV_CASE(80, 1, 1) GSN_CONV_CASE(32, 2, 2) }
+#undef GSN_CONV_CASE
+  if (d.ks == 3 && d.stride == 1) return launch_conv<NT, 3, 1, 0>(d, st);
+  if (d.ks == 3 && d.stride == 2) return launch_conv<NT, 3, 2, 0>(d, st);
+  if (d.ks == 1 && d.stride == 1) return launch_conv<NT, 1, 1, 0>(d, st);
+  if (d.ks == 2 && d.stride == 2) return launch_conv<NT, 2, 2, 0>(d, st);
   set_error("conv_mma: ks=%d stride=%d unsupported (3/1, 3/2, 1/1, 2/2)", d.ks, d.stride);
   return GSN_E_UNSUPPORTED;
 }
