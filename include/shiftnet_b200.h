@@ -52,7 +52,7 @@ typedef struct {
   const void *src[3];   /* NHWC fp16 (T,Hin,Win,src_c[i]) */
   int src_c[3];         /* padded channel count of each source (multiple of 8) */
   int cin_p;            /* sum of src_c, multiple of 16 */
-  int cout_p;           /* padded output channels: 16, 32, 48, 64 or 80 */
+  int cout_p;           /* padded output channels: 16, 32, 48, 64, 80 or 96 */
   int ks, stride, pad;  /* kernel size 1..3, stride 1..2, zero padding */
   const void *wpack;    /* fp16 weights in mma.m16n8k16 B-fragment order: [tap][cin_p/16][cout_p/8][32 lanes][4] */
   const float *bias;    /* cout_p floats or NULL */
@@ -62,6 +62,7 @@ typedef struct {
   int pixel_shuffle;    /* 1: dst is (T,2Hout,2Wout,cout_p/4), F.pixel_shuffle(.,2) fused into the store */
   float *chan_partial;  /* NULL or [T][tiles][cout_p] fp32: per-tile channel sums of the output (for CALayer) */
   void *dst;            /* NHWC fp16 */
+  int dst_c;            /* pixel_shuffle only: channel pitch of dst (0 = cout_p/4); channels >= cout_p/4 are not written */
 } GsnConvDesc;
 
 /* tiles per frame the conv kernel uses for chan_partial (16x16 output tiles) */
@@ -154,6 +155,27 @@ typedef struct {
 } GsnCabPassB;
 
 int gsn_cab_pass_b(const GsnCabPassB *d, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Width-generic pieces (C = 64 or 80) used by the Ours+ nets (gshift_deblur1.py / gshift_denoise1.py: C = 80,
+ * RepConv with groups of 8, gshift_deblur1.py:157-165), whose block is split at tensor boundaries:
+ *   gsn_shift_ln -> gsn_conv_mma (1x1, two halves) -> gsn_dw_gate -> gsn_group_conv5 -> gsn_conv_mma -> gsn_gate2
+ *   -> gsn_cab_fold -> gsn_cab_pass_b.
+ * ------------------------------------------------------------------------------------------- */
+/* [roll + shift gather + conv1] + LayerNorm -> out (T,H,W,cinp) fp16, cinp = pad16(C or 3C/2), padding channels 0.
+ * wc1: fp16 [9][C/2] (CAB2 modes); ln: fp32 gamma[cin] then beta[cin]. */
+int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
+                 void *out, int cinp, void *stream);
+/* g = (dw3x3(a)+a) * (dw3x3(b)+b) (RepConv2 + SimpleGate); wd fp16 [9][2C]; partial (optional) [T][tiles_linear][C]. */
+int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,
+                void *stream);
+/* z = a * sigmoid(b) (SimpleGate2) + per-tile channel sums [T][tiles_linear][C]. */
+int gsn_gate2(const void *a, const void *b, int T, int H, int W, int C, void *out, float *partial, void *stream);
+/* u = (conv5x5 + conv3x3 + id)(g), groups of 8 channels, times an optional per-frame channel scale [T][C] (fp32).
+ * wfrag: merged 5x5 taps in mma B-fragment order [C/8][13][32 lanes][4] fp16 (host/packing.py pack_group_conv5). */
+int gsn_group_conv5(const void *g, int T, int H, int W, int C, const void *wfrag, const float *scale, void *out, void *stream);
+/* y = clamped half-channel temporal roll of x (Shift_CAB.channel_shift, gshift_denoise1.py:167-179); C real of cp channels. */
+int gsn_roll_copy(const void *x, void *y, int T, int H, int W, int C, int cp, int reverse, void *stream);
 
 #ifdef __cplusplus
 }

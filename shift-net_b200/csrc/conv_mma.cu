@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
         } else {
           // F.pixel_shuffle(.,2): conv channel co = c*4 + i*2 + j -> dst[c, 2y+i, 2x+j]; co is even => j = 0 / 1
           const int co = n * 8 + tig * 2;
-          const int cd = cout_p >> 2, c = co >> 2, i = (co >> 1) & 1;
+          const int cd = d.dst_c ? d.dst_c : (cout_p >> 2), c = co >> 2, i = (co >> 1) & 1;
           const size_t sp = (((size_t)t * 2 * d.Hout + 2 * oy + i) * (2 * d.Wout) + 2 * ox) * cd + c;
           dst[sp] = __float2half_rn(v0);
           dst[sp + cd] = __float2half_rn(v1);
@@ -231,6 +231,7 @@ static int launch_conv_nt(const GsnConvDesc &d, cudaStream_t st) {
   if constexpr (NT == 4) { GSN_CONV_CASE(32, 3, 1) GSN_CONV_CASE(16, 3, 2) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 1, 1) GSN_CONV_CASE(96, 3, 1) GSN_CONV_CASE(64, 3, 1) }
   if constexpr (NT == 6) { GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(48, 3, 2) GSN_CONV_CASE(48, 1, 1) }
   if constexpr (NT == 8) { GSN_CONV_CASE(64, 3, 1) GSN_CONV_CASE(64, 3, 2) GSN_CONV_CASE(64, 1, 1) GSN_CONV_CASE(16, 2, 2) }
+  if constexpr (NT == 12) { GSN_CONV_CASE(80, 3, 1) }
   if constexpr (NT == 10) { GSN_CONV_CASE(80, 3, 1) GSN_CONV_CASE(80, 3, 2) GSN_CONV_CASE(80, 1, 1) GSN_CONV_CASE(32, 2, 2) }
 #undef GSN_CONV_CASE
   if (d.ks == 3 && d.stride == 1) return launch_conv<NT, 3, 1, 0>(d, st);
@@ -270,6 +271,7 @@ extern "C" int gsn_conv_mma(const GsnConvDesc *dp, void *stream) {
     case 48: return launch_conv_nt<6>(d, st);
     case 64: return launch_conv_nt<8>(d, st);
     case 80: return launch_conv_nt<10>(d, st);
-    default: set_error("conv_mma: cout_p=%d unsupported (16/32/48/64/80)", d.cout_p); return GSN_E_UNSUPPORTED;
+    case 96: return launch_conv_nt<12>(d, st);
+    default: set_error("conv_mma: cout_p=%d unsupported (16/32/48/64/80/96)", d.cout_p); return GSN_E_UNSUPPORTED;
   }
 }

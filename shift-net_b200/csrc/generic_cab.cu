@@ -1,0 +1,341 @@
+// Width-generic (C = 64 or 80) building blocks of the shift + NAF block, used by the Ours+ nets (C = 80, grouped
+// RepConv, gshift_deblur1.py / gshift_denoise1.py) whose 2C = 160 wide tensor does not fit the single fused tcgen05
+// kernel's TMEM/shared-memory budget.  The block is split at tensor boundaries, every piece is one of our kernels:
+//
+//   shift_ln      : temporal roll + spatial-shift gather + conv1 (dw3x3) + LayerNorm          -> A1 (T,H,W,pad16(C'))
+//   conv_mma 1x1  : first 1x1 as two half-width launches (a | b halves)                        (conv_mma.cu)
+//   dw_gate       : (dw3x3 + id)(a) * (dw3x3 + id)(b)  [+ per-tile sums for the denoise mid CA] -> g (T,H,W,C)
+//   group_conv5   : RepConv with groups of 8 channels (5x5 + 3x3 + id) on tensor cores (mma.sync, one n-tile per group)
+//   conv_mma 1x1  : second 1x1 (two halves), then gate2: a * sigmoid(b) + per-tile sums       -> z
+//   cab_fold / cab_pass_b (shift_cab.cu)
+//
+// Same zero-padding rules and the same deterministic per-tile partial sums as the fused path.
+#include "common.cuh"
+#include "shift_common.cuh"
+
+namespace gsn {
+
+__device__ __forceinline__ void shift_offset_rt(int C, int c, int &dy, int &dx) {
+  const int number = C / 2 / 8, n2 = (number - 1) / 2, n1 = number - 2 * n2;
+  if (c < 16 * n2) { const int g = c / n2; dy = kShiftOuter[g][0]; dx = kShiftOuter[g][1]; }
+  else { const int g = (c - 16 * n2) / n1; dy = kShiftInner[g][0]; dx = kShiftInner[g][1]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shift_ln: 16 lanes per pixel, lane = 8-channel chunk of the LayerNorm input [y_lo | y_hi | conv1(shift(hw))]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shift_ln_kernel(const __half *__restrict__ x, int T, int H, int W, int C, int mode,
+                                                       int circular, const __half *__restrict__ wc1 /*[9][C/2]*/,
+                                                       const float *__restrict__ ln /*gamma[CIN], beta[CIN]*/,
+                                                       __half *__restrict__ out, int cinp) {
+  const int lane16 = threadIdx.x & 15;
+  const long long hw = (long long)H * W;
+  const long long pix = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int t = blockIdx.y;
+  const bool shift = mode != GSN_MODE_CAB1;
+  const int HC = C / 2, cin = shift ? C + HC : C;
+  const bool active = pix < hw;
+  const int py = active ? (int)(pix / W) : 0, px = active ? (int)(pix - (long long)py * W) : 0;
+  const RollSrc rs = roll_source(mode, circular, t, T, C);
+  const size_t frame = (size_t)hw * C;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  const int cb = lane16 * 8;            // first channel of this lane's chunk inside the LN input
+  const bool has = active && cb < cin;
+  if (has) {
+    if (!shift) {
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(x + (size_t)t * frame + (size_t)pix * C + cb)), v);
+    } else if (cb < HC) {
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(x + rs.f_lo * frame + (size_t)pix * C + rs.c_lo + cb)), v);
+    } else if (cb < C) {
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(x + rs.f_hi * frame + (size_t)pix * C + rs.c_hi + cb - HC)), v);
+    } else {
+      // shifted half: neighbour frame's channels, per-channel (dy,dx), zero fill, then dw3x3 with zero padding
+      const bool fwd = mode == GSN_MODE_CAB2_FWD;
+      const __half *src = x + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = cb - C + i;
+        int dy, dx;
+        shift_offset_rt(C, c, dy, dx);
+        float a = 0.f;
+#pragma unroll
+        for (int ty = -1; ty <= 1; ++ty)
+#pragma unroll
+          for (int tx = -1; tx <= 1; ++tx) {
+            const int sy = py + ty, sx = px + tx;          // position in the shifted tensor
+            const int qy = sy - dy, qx = sx - dx;          // its source position
+            if (sy < 0 || sy >= H || sx < 0 || sx >= W || qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+            a = fmaf(__half2float(__ldg(src + ((size_t)qy * W + qx) * C + c)), __half2float(__ldg(wc1 + ((ty + 1) * 3 + tx + 1) * HC + c)), a);
+          }
+        v[i] = a;
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / cin;
+  float ss = 0.f;
+  if (cb < cin) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
+  }
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / cin + 1e-6f);
+  if (active && cb < cinp) {
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o8[i] = (cb < cin) ? (v[i] - mu) * rstd * __ldg(ln + cb + i) + __ldg(ln + cin + cb + i) : 0.f;
+    *reinterpret_cast<uint4 *>(out + ((size_t)t * hw + pix) * cinp + cb) = pack8(o8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dw_gate / gate2: 128 pixels x C/8 chunks per CTA, thread = (pixel slot, chunk); deterministic per-CTA channel sums
+// ---------------------------------------------------------------------------------------------------------------
+template <bool STENCIL>
+__global__ void __launch_bounds__(320) gate_kernel(const __half *__restrict__ a, const __half *__restrict__ b, int H, int W,
+                                                   int C, const __half *__restrict__ wd /*[9][2C] (STENCIL)*/,
+                                                   __half *__restrict__ out, float *__restrict__ partial) {
+  __shared__ float red[40 * 128];
+  const int nch = C / 8, slots = 320 / nch;            // C = 80: 10 chunks x 32 slots ; C = 64: 8 x 40
+  const int ch = threadIdx.x % nch, slot = threadIdx.x / nch;
+  const long long hw = (long long)H * W, p0 = (long long)blockIdx.x * 128;
+  const int t = blockIdx.y;
+  const size_t fo = (size_t)t * hw * C;
+  float sum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+  if (slot < slots) {
+    for (int k = slot; k < 128; k += slots) {
+      const long long p = p0 + k;
+      if (p >= hw) break;
+      float va[8], vb[8];
+      const size_t ce = fo + (size_t)p * C + ch * 8;
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(a + ce)), va);
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(b + ce)), vb);
+      float o[8];
+      if (STENCIL) {
+        const int y = (int)(p / W), xq = (int)(p - (long long)y * W);
+        float ra[8], rb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ra[i] = va[i]; rb[i] = vb[i]; }     // identity of RepConv2
+#pragma unroll
+        for (int ty = -1; ty <= 1; ++ty)
+#pragma unroll
+          for (int tx = -1; tx <= 1; ++tx) {
+            const int yy = y + ty, xx = xq + tx;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const size_t ne = fo + ((size_t)yy * W + xx) * C + ch * 8;
+            float na[8], nb[8], wa[8], wb[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(a + ne)), na);
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(b + ne)), nb);
+            const int tap = (ty + 1) * 3 + tx + 1;
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(wd + (size_t)tap * 2 * C + ch * 8)), wa);
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(wd + (size_t)tap * 2 * C + C + ch * 8)), wb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ra[i] = fmaf(na[i], wa[i], ra[i]); rb[i] = fmaf(nb[i], wb[i], rb[i]); }
+          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ra[i] * rb[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = va[i] * sigmoidf_fast(vb[i]);
+      }
+      *reinterpret_cast<uint4 *>(out + ce) = pack8(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum[i] += o[i];
+    }
+  }
+  if (partial) {
+    if (slot < slots) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[slot * 128 + ch * 8 + i] = sum[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+      float s = 0.f;
+      for (int q = 0; q < slots; ++q) s += red[q * 128 + threadIdx.x];
+      partial[((size_t)t * gridDim.x + blockIdx.x) * C + threadIdx.x] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// group_conv5: u = (conv5x5 + conv3x3 + id)(g) with groups of 8 channels, optional per-frame channel scale
+// (the denoise mid CALayer2 commutes with the grouped conv).  mma.sync m16n8k16: M = 16 pixels of a row, N = the 8
+// outputs of one group, K = (2 taps) x (8 inputs); 13 k-steps cover the 25 taps (+1 zero tap).
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__restrict__ gin, int H, int W,
+                                                             const uint2 *__restrict__ wfrag /*[C/8][13][32]*/,
+                                                             const float *__restrict__ scale /*[T][C] or null*/,
+                                                             __half *__restrict__ out) {
+  constexpr int NG = C / 8, TW = 20, PITCH = C + 8;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __half *tile = reinterpret_cast<__half *>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.z, ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16;
+  const size_t fo = (size_t)t * H * W * C;
+  for (int p = tid; p < TW * TW; p += 256) {
+    const int ly = p / TW, lx = p - ly * TW;
+    const int gy = oy0 + ly - 2, gx = ox0 + lx - 2;
+    const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const __half *sp = valid ? gin + fo + ((size_t)gy * W + gx) * C : gin;
+#pragma unroll
+    for (int ch = 0; ch < NG; ++ch) cp_async16(tile + (size_t)p * PITCH + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  float acc[2][NG][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < NG; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
+  const uint32_t tile_s = smem_u32(tile);
+  const int prow = (lane & 7) + ((lane >> 3) & 1) * 8;   // pixel (x) this lane addresses
+  const int tsel = lane >> 4;                            // 0: first tap of the pair, 1: second tap
+#pragma unroll 1
+  for (int ks = 0; ks < 13; ++ks) {
+    int tap = 2 * ks + tsel;
+    if (tap > 24) tap = 24;                              // 26th tap: weights are zero, any valid address will do
+    const int ky = tap / 5, kx = tap - ky * 5;
+#pragma unroll
+    for (int n = 0; n < NG; ++n) {
+      uint32_t a0[4], a1[4];
+      const uint32_t base = tile_s + (uint32_t)((((2 * warp + ky) * TW + prow + kx) * PITCH + n * 8) * 2);
+      ldmatrix_x4(a0[0], a0[1], a0[2], a0[3], base);
+      ldmatrix_x4(a1[0], a1[1], a1[2], a1[3], base + TW * PITCH * 2);
+      const uint2 b = __ldg(wfrag + ((size_t)n * 13 + ks) * 32 + lane);
+      mma16816(acc[0][n], a0, b.x, b.y);
+      mma16816(acc[1][n], a1, b.x, b.y);
+    }
+  }
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int oy = oy0 + 2 * warp + m;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int lx = g + hrow * 8, ox = ox0 + lx;
+      if (oy >= H || ox >= W) continue;
+      __half *dp = out + fo + ((size_t)oy * W + ox) * C + tig * 2;
+      const __half *cp = tile + ((2 * warp + m + 2) * TW + lx + 2) * PITCH + tig * 2;   // centre pixel: identity term
+#pragma unroll
+      for (int n = 0; n < NG; ++n) {
+        const float2 idv = unpack_half2(*reinterpret_cast<const uint32_t *>(cp + n * 8));
+        float v0 = acc[m][n][hrow * 2] + idv.x, v1 = acc[m][n][hrow * 2 + 1] + idv.y;
+        if (scale) {
+          v0 *= __ldg(scale + (size_t)t * C + n * 8 + tig * 2);
+          v1 *= __ldg(scale + (size_t)t * C + n * 8 + tig * 2 + 1);
+        }
+        *reinterpret_cast<uint32_t *>(dp + n * 8) = pack_half2(v0, v1);
+      }
+    }
+  }
+}
+
+// y = clamped temporal roll of x (Shift_CAB.channel_shift, gshift_denoise1.py:167-179); C real channels inside cp
+__global__ void __launch_bounds__(256) roll_copy_kernel(const __half *__restrict__ x, __half *__restrict__ y, int T,
+                                                        long long hw, int C, int cp, int reverse) {
+  const long long total = (long long)T * hw * cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cp);
+    const long long p = (i / cp) % hw;
+    const int t = (int)(i / cp / hw);
+    float v = 0.f;
+    if (c < C) {
+      const RollSrc rs = roll_source(reverse ? GSN_MODE_CAB2_REV : GSN_MODE_CAB2_FWD, 0, t, T, C);
+      const int h = C / 2;
+      const int f = c < h ? rs.f_lo : rs.f_hi, sc = c < h ? rs.c_lo + c : rs.c_hi + c - h;
+      v = __half2float(x[((size_t)f * hw + p) * cp + sc]);
+    }
+    y[i] = __float2half_rn(v);
+  }
+}
+
+}  // namespace gsn
+
+extern "C" int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
+                            void *out, int cinp, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(x && ln && out, "shift_ln: null pointer");
+  GSN_REQUIRE(C % 16 == 0 && C <= 80 && cinp % 8 == 0 && cinp <= 128 && T > 0 && H > 0 && W > 0, "shift_ln: bad sizes C=%d cinp=%d", C, cinp);
+  GSN_REQUIRE(mode == GSN_MODE_CAB1 || wc1, "shift_ln: conv1 weights missing");
+  const long long hw = (long long)H * W;
+  dim3 grid((unsigned)((hw + 15) / 16), T);
+  shift_ln_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(x), T, H, W, C, mode, circular, reinterpret_cast<const __half *>(wc1), ln,
+      reinterpret_cast<__half *>(out), cinp);
+  count_launch();
+  return check_launch("shift_ln");
+}
+
+extern "C" int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,
+                           void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(a && b && wd && out, "dw_gate: null pointer");
+  GSN_REQUIRE((C == 64 || C == 80) && T > 0 && H > 0 && W > 0, "dw_gate: C=%d unsupported", C);
+  const long long hw = (long long)H * W;
+  dim3 grid((unsigned)((hw + 127) / 128), T);
+  gate_kernel<true><<<grid, 320, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(a), reinterpret_cast<const __half *>(b), H, W, C, reinterpret_cast<const __half *>(wd),
+      reinterpret_cast<__half *>(out), partial);
+  count_launch();
+  return check_launch("dw_gate");
+}
+
+extern "C" int gsn_gate2(const void *a, const void *b, int T, int H, int W, int C, void *out, float *partial, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(a && b && out && partial, "gate2: null pointer");
+  GSN_REQUIRE((C == 64 || C == 80) && T > 0 && H > 0 && W > 0, "gate2: C=%d unsupported", C);
+  const long long hw = (long long)H * W;
+  dim3 grid((unsigned)((hw + 127) / 128), T);
+  gate_kernel<false><<<grid, 320, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(a), reinterpret_cast<const __half *>(b), H, W, C, nullptr, reinterpret_cast<__half *>(out),
+      partial);
+  count_launch();
+  return check_launch("gate2");
+}
+
+extern "C" int gsn_group_conv5(const void *g, int T, int H, int W, int C, const void *wfrag, const float *scale, void *out,
+                               void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(g && wfrag && out, "group_conv5: null pointer");
+  GSN_REQUIRE(T > 0 && H > 0 && W > 0, "group_conv5: empty shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((W + 15) / 16, (H + 15) / 16, T);
+  if (C == 80) {
+    const size_t smem = 20 * 20 * (80 + 8) * 2;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(group_conv5_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    group_conv5_kernel<80><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(g), H, W,
+                                                    reinterpret_cast<const uint2 *>(wfrag), scale, reinterpret_cast<__half *>(out));
+  } else {
+    set_error("group_conv5: C=%d unsupported (80)", C);
+    return GSN_E_UNSUPPORTED;
+  }
+  count_launch();
+  return check_launch("group_conv5");
+}
+
+extern "C" int gsn_roll_copy(const void *x, void *y, int T, int H, int W, int C, int cp, int reverse, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(x && y && T > 0 && H > 0 && W > 0 && C % 2 == 0 && C <= cp, "roll_copy: bad arguments");
+  const long long hw = (long long)H * W, total = (long long)T * hw * cp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  roll_copy_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(x), reinterpret_cast<__half *>(y), T, hw, C, cp, reverse);
+  count_launch();
+  return check_launch("roll_copy");
+}

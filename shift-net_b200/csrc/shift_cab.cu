@@ -409,9 +409,8 @@ __global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__
 template <int C>
 __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, NT = C / 8;
-  __shared__ __align__(128) unsigned char sz[KC * PZ];
-  __shared__ __align__(128) unsigned char ss[KC * PZ];
-  __shared__ __align__(128) unsigned char sw[KC * C * 16];
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  unsigned char *sz = smem_b, *ss = smem_b + KC * PZ, *sw = smem_b + 2 * KC * PZ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
   const long long hw = (long long)d.H * d.W, p0 = (long long)blockIdx.x * MP;
@@ -708,9 +707,17 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   const long long hw = (long long)d.H * d.W;
   dim3 grid((unsigned)((hw + 127) / 128), d.T);
   if (d.C == 64) {
-    cab_pass_b_kernel<64><<<grid, 256, 0, st>>>(d);
+    constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cab_pass_b_kernel<64><<<grid, 256, smem, st>>>(d);
+  } else if (d.C == 80) {
+    constexpr int smem = 2 * 10 * 129 * 16 + 10 * 80 * 16;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cab_pass_b_kernel<80><<<grid, 256, smem, st>>>(d);
   } else {
-    set_error("cab_pass_b: C=%d unsupported (64)", d.C);
+    set_error("cab_pass_b: C=%d unsupported (64, 80)", d.C);
     return GSN_E_UNSUPPORTED;
   }
   count_launch();

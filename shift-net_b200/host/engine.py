@@ -20,10 +20,6 @@ class Engine:
     def __init__(self, spec, state_dict, device):
         if torch.device(device).type != "cuda":
             raise RuntimeError("shiftnet_b200: the engine runs on CUDA only (no CPU fallback)")
-        if spec.plus:
-            raise NotImplementedError(
-                f"shiftnet_b200: arch {spec.name} (Ours+: C=80, grouped RepConv, 3-level stage 1) is not implemented in "
-                "the CUDA path yet -- gshift_deblur2 and gshift_denoise2 run")
         self.spec = spec
         self.dev = torch.device(device)
         self.lib = L.load()
@@ -85,8 +81,13 @@ class Engine:
             b = self.sd.get(key + ".bias")
             self.cache[ck] = (wp, P.pack_bias(b, cout_p) if b is not None else None)
         wp, bias = self.cache[ck]
+        dst_c = 0
         if pixel_shuffle:
-            dst = self._new(T, 2 * Hout, 2 * Wout, cout_p // 4)
+            dst_c = P.pad16(cout // 4)
+            if dst_c == cout_p // 4:
+                dst = self._new(T, 2 * Hout, 2 * Wout, dst_c)
+            else:                                   # padding channels are never written by the shuffle store
+                dst = torch.zeros(T, 2 * Hout, 2 * Wout, dst_c, dtype=torch.float16, device=self.dev)
         else:
             dst = self._new(T, Hout, Wout, cout_p)
         partial = None
@@ -108,6 +109,7 @@ class Engine:
         d.pixel_shuffle = 1 if pixel_shuffle else 0
         d.chan_partial = partial.data_ptr() if partial is not None else None
         d.dst = dst.data_ptr()
+        d.dst_c = dst_c
         with self._timed("conv_mma", T * Hout * Wout):
             L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
         return (dst, partial) if want_sums else dst
@@ -172,9 +174,84 @@ class Engine:
         return self.seq_cabs(p + ".decoder_level1", y, c1)
 
     # ------------------------------------------------------------------ fused shift + NAF block
+    def _fold_and_pass_b(self, p, x, z, partial, ntiles, fw, mode):
+        T, H, W, Cc = x.shape
+        weff = self._new(T, Cc * Cc)
+        beff = self._new(T, Cc, dtype=torch.float32)
+        L.check(self.lib.gsn_cab_fold(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["du0"].data_ptr(), fw["du2"].data_ptr(),
+                                      fw["du0"].shape[0], fw["w3"].data_ptr(), fw["beta"].data_ptr(),
+                                      fw["bias3"].data_ptr() if fw["bias3"] is not None else None, Cc, T, weff.data_ptr(),
+                                      beff.data_ptr(), self._stream()), "cab_fold")
+        out = self._new(T, H, W, Cc)
+        b = L.CabPassB()
+        b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
+        b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
+        with self._timed("cab_pass_b", T * H * W):
+            L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
+        return out
+
+    def gated_cab_generic(self, p, x, mode):
+        """Width-generic CAB1/CAB2 (Ours+, C=80, grouped RepConv): the block split at tensor boundaries
+        (csrc/generic_cab.cu): shift_ln -> 1x1 (a|b) -> dw_gate -> group_conv5 -> 1x1 (a|b) -> gate2 -> fold -> pass B."""
+        T, H, W, Cc = x.shape
+        shift = mode != L.MODE_CAB1
+        k = self.boff
+        sd = self.sd
+        ck = ("gcabg", p)
+        if ck not in self.cache:
+            ln = torch.cat((sd[p + ".norm.weight"], sd[p + ".norm.bias"])).contiguous()
+            wc1 = sd[p + ".conv1.weight"].view(Cc // 2, 9).t().contiguous().half() if shift else None
+            w1 = sd[p + ".body.0.weight"]
+            sd[p + ".body.0#a.weight"], sd[p + ".body.0#b.weight"] = w1[:Cc].contiguous(), w1[Cc:].contiguous()
+            wd = sd[p + ".body.1.conv_2.weight"].view(2 * Cc, 9).t().contiguous().half()
+            rp = p + f".body.{3 + k}"
+            wfrag = P.pack_group_conv5(sd[rp + ".conv_1.weight"], sd[rp + ".conv_2.weight"])
+            w2 = sd[p + f".body.{4 + k}.weight"]
+            sd[p + f".body.{4 + k}#a.weight"], sd[p + f".body.{4 + k}#b.weight"] = w2[:Cc].contiguous(), w2[Cc:].contiguous()
+            self.cache[ck] = (ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k))
+        ln, wc1, wd, wfrag, fw = self.cache[ck]
+        cin = Cc + Cc // 2 if shift else Cc
+        cinp = P.pad16(cin)
+        a1 = self._new(T, H, W, cinp)
+        with self._timed("shift_ln", T * H * W):
+            L.check(self.lib.gsn_shift_ln(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0,
+                                          wc1.data_ptr() if wc1 is not None else None, ln.data_ptr(), a1.data_ptr(), cinp,
+                                          self._stream()), "shift_ln " + p)
+        ga = self.conv(p + ".body.0#a", [a1], [cin], Cc)
+        gb = self.conv(p + ".body.0#b", [a1], [cin], Cc)
+        ntl = self.lib.gsn_cab_tiles_linear(H * W)
+        g = self._new(T, H, W, Cc)
+        pg = self._new(T, ntl, Cc, dtype=torch.float32) if self.spec.denoise else None
+        L.check(self.lib.gsn_dw_gate(ga.data_ptr(), gb.data_ptr(), T, H, W, Cc, wd.data_ptr(), g.data_ptr(),
+                                     pg.data_ptr() if pg is not None else None, self._stream()), "dw_gate")
+        s1 = None
+        if self.spec.denoise:        # mid CALayer2: its per-channel scale commutes with the grouped RepConv
+            s1 = self._new(T, Cc, dtype=torch.float32)
+            L.check(self.lib.gsn_ca_scale(pg.data_ptr(), ntl, 1.0 / (H * W), fw["mid_du0"].data_ptr(), fw["mid_du2"].data_ptr(),
+                                          Cc, fw["mid_du0"].shape[0], Cc, T, s1.data_ptr(), self._stream()), "mid ca_scale")
+        u = self._new(T, H, W, Cc)
+        with self._timed("group_conv5", T * H * W):
+            L.check(self.lib.gsn_group_conv5(g.data_ptr(), T, H, W, Cc, wfrag.data_ptr(),
+                                             s1.data_ptr() if s1 is not None else None, u.data_ptr(), self._stream()), "group_conv5")
+        va = self.conv(p + f".body.{4 + k}#a", [u], [Cc], Cc)
+        vb = self.conv(p + f".body.{4 + k}#b", [u], [Cc], Cc)
+        z = self._new(T, H, W, Cc)
+        partial = self._new(T, ntl, Cc, dtype=torch.float32)
+        L.check(self.lib.gsn_gate2(va.data_ptr(), vb.data_ptr(), T, H, W, Cc, z.data_ptr(), partial.data_ptr(), self._stream()), "gate2")
+        return self._fold_and_pass_b(p, x, z, partial, ntl, fw, mode)
+
+    def shift_cab(self, p, x, c, reverse):
+        """Shift_CAB of Ours+ denoise (gshift_denoise1.py:157-186): clamped temporal roll, then the CAB body."""
+        T, H, W, cp = x.shape
+        y = self._new(T, H, W, cp)
+        L.check(self.lib.gsn_roll_copy(x.data_ptr(), y.data_ptr(), T, H, W, c, cp, 1 if reverse else 0, self._stream()), "roll_copy")
+        return self.cab(p, y, c)
+
     def gated_cab(self, p, x, mode, debug_stage=0):
         """One CAB2 (mode fwd/rev: shift folded into the load) or CAB1 step: pass A -> fold -> pass B."""
         T, H, W, Cc = x.shape
+        if Cc != 64:
+            return self.gated_cab_generic(p, x, mode)
         shift = mode != L.MODE_CAB1
         ck = ("gcab", p)
         if ck not in self.cache:
@@ -206,18 +283,7 @@ class Engine:
             with self._timed("cab_pass_a2", T * H * W):
                 L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2eff.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc,
                                                  self._stream()), "cab_pass_a2")
-        weff = self._new(T, Cc * Cc)
-        beff = self._new(T, Cc, dtype=torch.float32)
-        L.check(self.lib.gsn_cab_fold(partial.data_ptr(), ntiles, 1.0 / (H * W), fw["du0"].data_ptr(), fw["du2"].data_ptr(),
-                                      fw["du0"].shape[0], fw["w3"].data_ptr(), fw["beta"].data_ptr(),
-                                      fw["bias3"].data_ptr() if fw["bias3"] is not None else None, Cc, T, weff.data_ptr(),
-                                      beff.data_ptr(), self._stream()), "cab_fold")
-        out = self._new(T, H, W, Cc)
-        b = L.CabPassB()
-        b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, a.circular
-        b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
-        with self._timed("cab_pass_b", T * H * W):
-            L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
+        out = self._fold_and_pass_b(p, x, z, partial, ntiles, fw, mode)
         if debug_stage:
             return out, z, dbg
         return out
@@ -234,6 +300,8 @@ class Engine:
     def stage1(self, p, x):
         """gshift_deblur2.py:587-613 / gshift_denoise2.py:583-609."""
         sp = self.spec
+        if sp.plus:
+            return self.stage1_plus(p, x)
         n0, c = sp.n0, sp.c1
         x = self.cab(p + ".concat", x, n0)
         shortcut = x
@@ -255,6 +323,38 @@ class Engine:
         else:
             up = self.conv(p + ".upsample0.upsample_conv", [y], [c], 4 * n0, pixel_shuffle=True, prelu_key=p + ".act.weight")
             out = self.conv(p + ".conv_hr0", [up], [n0], n0, residual=sk)                 # gshift_deblur2.py:611
+        return self.cab(p + ".out_conv", out, n0)
+
+    def stage1_plus(self, p, x):
+        """Encoder2 of Ours+ (gshift_deblur1.py:614-643 ; gshift_denoise1.py:640-671): plain/Shift CABs going down three
+        levels, shift blocks (C=80) on the way up."""
+        sp = self.spec
+        n0, c = sp.n0, sp.c1
+        x = self.cab(p + ".concat", x, n0)
+        shortcut = x
+        if sp.denoise:
+            x = self.shift_cab(p + ".encoder_level0", x, n0, False)
+            x = self.shift_cab(p + ".encoder_level0_1", x, n0, True)
+        y = self.conv(p + ".down01.0", [x], [n0], c, stride=2, pad=0, prelu_key=p + ".down01.1.weight")
+        if sp.denoise:
+            enc11 = self.shift_cab(p + ".encoder_level1_1", self.shift_cab(p + ".encoder_level1", y, c, False), c, True)
+        else:
+            enc11 = self.cab(p + ".encoder_level1_1", self.cab(p + ".encoder_level1", y, c), c)
+        y = self.downsample(p + ".down12", enc11, c, c)
+        enc22 = self.cab(p + ".encoder_level2_1", self.cab(p + ".encoder_level2", y, c), c)
+        y = self.downsample(p + ".down23", enc22, c, c)
+        y = self.cab(p + ".encoder_level3_1", self.cab(p + ".encoder_level3", y, c), c)
+        y = self.shift_block(p + ".decoder_level3", y)
+        y = self.shift_block(p + ".decoder_level3_1", y)
+        y = self.skip_upsample(p + ".up32", y, c, self.cab(p + ".skip_attn2", enc22, c), c)
+        y = self.shift_block(p + ".decoder_level2", y)
+        y = self.shift_block(p + ".decoder_level2_1", y)
+        y = self.skip_upsample(p + ".up21", y, c, self.cab(p + ".skip_attn1", enc11, c), c)
+        for n in ("decoder_level1", "decoder_level1_1", "decoder_level1_2"):
+            y = self.shift_block(f"{p}.{n}", y)
+        sk = self.cab(p + ".skip_conv", shortcut, n0)
+        up = self.conv(p + ".upsample0.upsample_conv", [y], [c], 4 * n0, pixel_shuffle=True)
+        out = self.conv(p + ".conv_hr0", [up, sk], [n0, n0], n0)                          # gshift_deblur1.py:640
         return self.cab(p + ".out_conv", out, n0)
 
     # ------------------------------------------------------------------ whole net

@@ -14,6 +14,7 @@ EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
+    "gsn_shift_ln", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
 ]
 
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
@@ -27,6 +28,7 @@ class ConvDesc(C.Structure):
         ("cin_p", C.c_int), ("cout_p", C.c_int), ("ks", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("wpack", C.c_void_p), ("bias", C.c_void_p), ("has_prelu", C.c_int), ("prelu_slope", C.c_float),
         ("residual", C.c_void_p), ("pixel_shuffle", C.c_int), ("chan_partial", C.c_void_p), ("dst", C.c_void_p),
+        ("dst_c", C.c_int),
     ]
 
 
@@ -77,6 +79,11 @@ def load():
     lib.gsn_cab_fold_mid.argtypes = [vp, i, f, vp, vp, i, vp, i, i, vp, vp]
     lib.gsn_cab_tiles_linear.argtypes = [ll]
     lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    lib.gsn_shift_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, i, vp]
+    lib.gsn_dw_gate.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
+    lib.gsn_gate2.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
+    lib.gsn_group_conv5.argtypes = [vp, i, i, i, i, vp, vp, vp, vp]
+    lib.gsn_roll_copy.argtypes = [vp, vp, i, i, i, i, i, i, vp]
     for n in EXPORTS:
         fn = getattr(lib, n)
         if fn.restype is C.c_int and n not in ("gsn_version", "gsn_conv_tiles", "gsn_cab_tiles"):

@@ -107,3 +107,16 @@ def pack_cab_fold(sd, p, body_off=0):
         d["mid_du2"] = sd[p + ".body.3.conv_du.2.weight"].float().flatten(1).contiguous()
         d["w2"] = sd[p + f".body.{4 + k}.weight"].float().flatten(1).contiguous()
     return d
+
+
+def pack_group_conv5(w5, w3):
+    """Grouped RepConv taps (C, 8, 5, 5) + (C, 8, 3, 3) (gshift_deblur1.py:160-161) -> merged 5x5, fp16 mma B fragments
+    [C/8 groups][13 k-steps = tap pairs][32 lanes][b0 (tap 2k), b1 (tap 2k+1)] (csrc/generic_cab.cu group_conv5)."""
+    w = w5.float().clone()
+    w[:, :, 1:4, 1:4] += w3.float()
+    C = w.shape[0]
+    wm = torch.zeros(C, 8, 26, device=w.device)
+    wm[:, :, :25] = w.reshape(C, 8, 25)
+    v = wm.view(C // 8, 8, 4, 2, 13, 2)            # (group, n, tig, e, kstep, tsel) ; cin = 2*tig + e ; tap = 2*kstep + tsel
+    v = v.permute(0, 4, 1, 2, 5, 3).contiguous()   # (group, kstep, n, tig, tsel, e) -> lane = n*4 + tig, regs (b0, b1)
+    return v.reshape(-1).half()

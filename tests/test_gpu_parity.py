@@ -47,7 +47,7 @@ def check(a, ref, tol, what):
     assert r < tol, (what, r, m)
 
 
-CUDA_ARCHS = ["gshift_deblur2", "gshift_denoise2"]       # archs whose CUDA path exists (Ours+ raises NotImplementedError)
+CUDA_ARCHS = ["gshift_deblur2", "gshift_denoise2", "gshift_deblur1", "gshift_denoise1"]
 
 
 def _make_env(arch):
@@ -278,14 +278,6 @@ def test_full_size_cyclic_frame_equivariance(env):
     assert torch.equal(b[1:], a[:-1])
     # and the run is deterministic
     assert torch.equal(net(x), a)
-
-
-def test_ours_plus_fails_loudly():
-    """Ours+ has no CUDA path yet: it must raise, never fall back."""
-    sd, spec = gio.synthetic_checkpoint("gshift_deblur1")
-    net = _net(sd, arch="gshift_deblur1")
-    with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 6, 3, 32, 32, device=DEV, dtype=torch.float16))
 
 
 def test_denoise_entry_point_synthetic(tmp_path):
