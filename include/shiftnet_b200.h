@@ -122,10 +122,16 @@ typedef struct {
                            RepConv).  A per-channel scale commutes with the depthwise RepConv, so with mid_ca=1 pass A
                            stops after the RepConv: ``z`` receives u = RepConv(gate) (C ch) and ``chan_partial`` the
                            per-tile sums of the gated tensor; gsn_cab_fold_mid + gsn_cab_pass_a2 finish the block. */
+  const void *hw_pre;   /* CAB2 modes: NULL = the shift gather + conv1 run inside pass A (bounding box in smem);
+                           non-NULL = (T,H,W,C/2) fp16 from gsn_shift_conv1, read in the LayerNorm load stage */
 } GsnCabPassA;
 
 int gsn_cab_tiles(int mode, int H, int W);
 int gsn_cab_pass_a(const GsnCabPassA *d, void *stream);
+
+/* Grouped spatial-temporal shift folded into the load stage of conv1 (dw3x3): out = conv1(spatial_shift2(hw)) with hw the
+ * neighbour frame's half of the channels (d2:465-519, 226,254); out (T,H,W,C/2) fp16.  wc1: fp16 [9][C/2]. */
+int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, void *out, void *stream);
 
 /* mid fold (denoise): w2eff[t] = W2 diag(s1_t) as fp16 [T][C/8][2C][8], s1 from the mid CALayer2 on mean(gated).
  * w_du0 [cr][C], w_du2 [C][cr], w2 [2C][C] (fp32). */

@@ -118,7 +118,9 @@ __device__ __forceinline__ void h8_mul(H8 &acc, const H8 &a, const H8 &w) {
 }
 
 // ---- configuration ----------------------------------------------------------------------------------
-template <int C, bool SHIFT>
+// SHIFT: CAB2 (LayerNorm input = [rolled stream | conv1(shifted half)]).  BOX: the gather runs inside this kernel (bounding
+// box staged in smem); SHIFT && !BOX: the shifted+conv1'd half was produced by shift_conv1_kernel and is read from HBM.
+template <int C, bool SHIFT, bool BOX = SHIFT>
 struct TcCfg {
   static constexpr int TW = 16, TH = 16;
   static constexpr int HC = C / 2;
@@ -153,7 +155,7 @@ struct TcCfg {
   static constexpr int S_A1 = S_W1 + W1_BYTES;
   static constexpr int A1_BYTES = KC1 * P1;
   static constexpr int S_R = (S_A1 + A1_BYTES + 127) / 128 * 128;
-  static constexpr int R12_BYTES = SHIFT ? BW * BH * HC * 2 : 0;
+  static constexpr int R12_BYTES = BOX ? BW * BH * HC * 2 : 0;
   static constexpr int S_G1 = S_W1;
   static constexpr int G1_BYTES = NC * P1;
   static constexpr int S_GT = ((S_G1 + G1_BYTES > S_R ? S_G1 + G1_BYTES : S_R) + 127) / 128 * 128;
@@ -165,15 +167,15 @@ struct TcCfg {
   static constexpr int S_A2 = S_G1;                                  // GEMM2 operand, then the z staging tile
   static_assert(2 * CIN * 4 <= 1024 && 9 * HC * 2 <= 704, "X region layout");
   static_assert(KC2 * P3 <= G1_BYTES, "A2 aliases G1");
-  static_assert(!SHIFT || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box, not over A1/W1");
-  static_assert(SHIFT || S_WT2 >= S_A1 + A1_BYTES, "WT2 must not overlap A1 while GEMM1 reads it");
+  static_assert(!BOX || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box, not over A1/W1");
+  static_assert(BOX || S_WT2 >= S_A1 + A1_BYTES, "WT2 must not overlap A1 while GEMM1 reads it");
   static_assert(S_A1 + (KC1 - 1) * P1 + (MT1 * 128) * 16 <= SMEM, "UMMA rows beyond M1 must stay inside the allocation");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int C, bool SHIFT, bool MIDCA>
+template <int C, bool SHIFT, bool MIDCA, bool BOX>
 __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnCabPassA d, const ShiftTable tab) {
-  using K = TcCfg<C, SHIFT>;
+  using K = TcCfg<C, SHIFT, BOX>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.z, x0 = blockIdx.x * K::TW, y0 = blockIdx.y * K::TH;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       cp_async16(dst, wb + off, true);
     }
     for (int i = tid; i < K::W1_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
-    if (SHIFT) {
+    if (BOX) {
       const bool fwd = d.mode == GSN_MODE_CAB2_FWD;
       const __half *src = xg + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
       constexpr int CH = K::HC / 8;
@@ -232,8 +234,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   const uint32_t tmem = *tmem_slot;
   GSN_CLK();  // 1: loads landed
 
-  // ---- P1a (SHIFT): per-channel spatial-shift gather fused with conv1 (dw3x3, zero pad) -> raw A1 planes --------
-  if (SHIFT) {
+  // ---- P1a (BOX): per-channel spatial-shift gather fused with conv1 (dw3x3, zero pad) -> raw A1 planes --------
+  if (BOX) {
     const __half *wc1 = reinterpret_cast<const __half *>(smem + K::S_X + K::X_C1);
     const __half *r12 = reinterpret_cast<const __half *>(smem + K::S_R);
     constexpr int SEG = K::R1W / 2;  // 11-pixel row segments
@@ -330,19 +332,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     for (int k = 0; k < NV / 8; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { gam[k * 8 + i] = ln_g[chunk_of[k] * 8 + i]; bet[k * 8 + i] = ln_b[chunk_of[k] * 8 + i]; }
-    uint4 raw[NIT][2];
+    constexpr int PB = (SHIFT && !BOX) ? 2 : NIT;    // items whose loads are in flight together (register budget)
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {               // issue every global load first (memory-level parallelism)
+    for (int it0 = 0; it0 < NIT; it0 += PB) {
+    uint4 raw[NIT][(SHIFT && !BOX) ? 3 : 2];
+#pragma unroll
+    for (int it = it0; it < it0 + PB && it < NIT; ++it) {   // issue the batch's global loads first (memory-level parallelism)
       const int q = (tid + it * kTcThreads) >> 2;
       const int ry = q / K::R1W, rx = q - ry * K::R1W;
       const int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
       const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
       raw[it][0] = raw[it][1] = make_uint4(0, 0, 0, 0);
+      if (SHIFT && !BOX) raw[it][(SHIFT && !BOX) ? 2 : 0] = make_uint4(0, 0, 0, 0);
       if (inimg) {
         const size_t pix = ((size_t)gy * d.W + gx) * C;
         if (SHIFT) {
           raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8));
           raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8));
+          if (!BOX) raw[it][(SHIFT && !BOX) ? 2 : 0] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(d.hw_pre) + ((size_t)t * d.H * d.W + (size_t)gy * d.W + gx) * K::HC + j * 8));
         } else {
           raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16));
           raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8));
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       }
     }
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
+    for (int it = it0; it < it0 + PB && it < NIT; ++it) {
       const int item = tid + it * kTcThreads;
       if (item < ITEMS) {                            // warp-uniform (ITEMS is a multiple of 32)
         const int q = item >> 2;
@@ -360,7 +367,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
         float v[NV];
         unpack8(raw[it][0], *reinterpret_cast<float(*)[8]>(&v[0]));
         unpack8(raw[it][1], *reinterpret_cast<float(*)[8]>(&v[8]));
-        if (SHIFT) {
+        if (SHIFT && !BOX) {
+          unpack8(raw[it][(SHIFT && !BOX) ? 2 : 0], *reinterpret_cast<float(*)[8]>(&v[SHIFT ? 16 : 0]));
+        } else if (SHIFT) {
           if (inimg) unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A1 + (C / 8 + j) * K::P1 + q * 16), *reinterpret_cast<float(*)[8]>(&v[16]));
           else {
 #pragma unroll
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
         }
       }
     }
+    }
     fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
     __syncthreads();
     GSN_CLK();  // LN done
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     umma_commit(bar);
   }
-  if (SHIFT) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather)
+  if (BOX) cp_async_wait<0>();     // phase-2 weights landed (issued after the gather)
   mbar_wait(bar, 0);
   tc_fence_after();
   __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
@@ -706,29 +716,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
 }
 
-template <int C, bool SHIFT, bool MIDCA>
+template <int C, bool SHIFT, bool MIDCA, bool BOX>
 static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st) {
-  using K = TcCfg<C, SHIFT>;
+  using K = TcCfg<C, SHIFT, BOX>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT, MIDCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     attr_set = true;
   }
   static const ShiftTable tab = make_shift_table(C);
   dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + K::TH - 1) / K::TH, d.T);
-  cab_pass_a_tc_kernel<C, SHIFT, MIDCA><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
+  cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
   count_launch();
   return check_launch("cab_pass_a_tc");
 }
 
 int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st) {
   if (d.C == 64) {
+    const bool split = d.hw_pre != nullptr;      // shifted half precomputed by gsn_shift_conv1
     if (d.mid_ca) {
-      if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, true>(d, st);
-      return launch_pass_a_tc<64, true, true>(d, st);
+      if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, true, false>(d, st);
+      return split ? launch_pass_a_tc<64, true, true, false>(d, st) : launch_pass_a_tc<64, true, true, true>(d, st);
     }
-    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, false>(d, st);
-    return launch_pass_a_tc<64, true, false>(d, st);
+    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, false, false>(d, st);
+    return split ? launch_pass_a_tc<64, true, false, false>(d, st) : launch_pass_a_tc<64, true, false, true>(d, st);
   }
   set_error("cab_pass_a: C=%d unsupported (64)", d.C);
   return GSN_E_UNSUPPORTED;

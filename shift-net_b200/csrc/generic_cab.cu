@@ -244,6 +244,85 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// shift_conv1: out = conv1(spatial_shift2(neighbour half))   -- the gather folded into the load stage of the dw3x3.
+// 16x16-pixel tiles, the 34x34x(C/2) source box staged with zero-filling cp.async, per-channel sliding windows,
+// results staged in smem and written with 16-byte stores.  Memory/L2 bound; 2 CTAs per SM overlap load and compute.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256, 2) shift_conv1_kernel(const __half *__restrict__ x, int T, int H, int W, int mode,
+                                                             int circular, const __half *__restrict__ wc1,
+                                                             __half *__restrict__ out) {
+  constexpr int HC = C / 2, CH = HC / 8, TS = 16, BW = TS + 18;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __half *box = reinterpret_cast<__half *>(smem);                       // [BW*BW][HC]
+  __half *ot = reinterpret_cast<__half *>(smem + BW * BW * HC * 2);     // [TS*TS][HC]
+  const int tid = threadIdx.x;
+  const int t = blockIdx.z, x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  const RollSrc rs = roll_source(mode, circular, t, T, C);
+  const size_t frame = (size_t)H * W * C;
+  const bool fwd = mode == GSN_MODE_CAB2_FWD;
+  const __half *src = x + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
+  for (int p = tid; p < BW * BW; p += 256) {
+    const int by = p / BW, bx = p - by * BW;
+    const int gy = y0 - 9 + by, gx = x0 - 9 + bx;
+    const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const __half *sp = valid ? src + ((size_t)gy * W + gx) * C : src;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) cp_async16(box + (size_t)p * HC + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const bool interior = y0 >= 1 && y0 + TS + 1 <= H && x0 >= 1 && x0 + TS + 1 <= W;   // all destination taps in-image
+  for (int item = tid; item < HC * TS; item += 256) {
+    const int c = item % HC, oy = item / HC;
+    int dy, dx;
+    shift_offset<C>(c, dy, dx);
+    float w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = __half2float(__ldg(wc1 + i * HC + c));
+    const __half *rp = box + ((oy - 1 - dy + 9) * BW - dx + 9) * HC + c;   // (row oy+ty-1, col) -> rp[(ty*BW + col) * HC]
+    bool rowok[3];
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) { const int sy = y0 + oy + ty - 1; rowok[ty] = interior || (sy >= 0 && sy < H); }
+    float v[3][3];
+    auto load_col = [&](int col, float(&o)[3]) {
+      const int sx = x0 + col;
+      const bool cok = interior || (sx >= 0 && sx < W);
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) o[ty] = (cok && rowok[ty]) ? __half2float(rp[(ty * BW + col) * HC]) : 0.f;
+    };
+    {
+      float a[3], b[3];
+      load_col(-1, a);
+      load_col(0, b);
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) { v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+    }
+#pragma unroll
+    for (int ox = 0; ox < TS; ++ox) {
+      float nc[3];
+      load_col(ox + 1, nc);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) { v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty]; }
+      a0 = fmaf(v[0][0], w[0], fmaf(v[0][1], w[1], v[0][2] * w[2]));
+      a1 = fmaf(v[1][0], w[3], fmaf(v[1][1], w[4], v[1][2] * w[5]));
+      a2 = fmaf(v[2][0], w[6], fmaf(v[2][1], w[7], v[2][2] * w[8]));
+      ot[(oy * TS + ox) * HC + c] = __float2half_rn(a0 + a1 + a2);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < TS * TS * CH; i += 256) {
+    const int ch = i % CH, p = i / CH;
+    const int gy = y0 + p / TS, gx = x0 + (p % TS);
+    if (gy < H && gx < W)
+      *reinterpret_cast<uint4 *>(out + (((size_t)t * H + gy) * W + gx) * HC + ch * 8) = *reinterpret_cast<const uint4 *>(ot + (size_t)p * HC + ch * 8);
+  }
+}
+
 // y = clamped temporal roll of x (Shift_CAB.channel_shift, gshift_denoise1.py:167-179); C real channels inside cp
 __global__ void __launch_bounds__(256) roll_copy_kernel(const __half *__restrict__ x, __half *__restrict__ y, int T,
                                                         long long hw, int C, int cp, int reverse) {
@@ -264,6 +343,24 @@ __global__ void __launch_bounds__(256) roll_copy_kernel(const __half *__restrict
 }
 
 }  // namespace gsn
+
+extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, void *out,
+                               void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(x && wc1 && out, "shift_conv1: null pointer");
+  GSN_REQUIRE(T > 0 && H > 0 && W > 0, "shift_conv1: empty shape");
+  GSN_REQUIRE(mode == GSN_MODE_CAB2_FWD || mode == GSN_MODE_CAB2_REV, "shift_conv1: mode=%d is not a shift mode", mode);
+  if (C != 64) { set_error("shift_conv1: C=%d unsupported (64)", C); return GSN_E_UNSUPPORTED; }
+  constexpr int smem = 34 * 34 * 32 * 2 + 16 * 16 * 32 * 2;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(shift_conv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  dim3 grid((W + 15) / 16, (H + 15) / 16, T);
+  shift_conv1_kernel<64><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(x), T, H, W, mode, circular, reinterpret_cast<const __half *>(wc1),
+      reinterpret_cast<__half *>(out));
+  count_launch();
+  return check_launch("shift_conv1");
+}
 
 extern "C" int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
                             void *out, int cinp, void *stream) {

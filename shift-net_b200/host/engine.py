@@ -26,6 +26,10 @@ class Engine:
         self.sd = {k: v.detach().to(self.dev, torch.float32) for k, v in state_dict.items()}
         self.cache = {}
         self.boff = 1 if spec.denoise else 0
+        # CAB2 front end: "fused" = gather + conv1 inside pass A (box in smem); "split" = gsn_shift_conv1 writes the
+        # shifted+conv1'd half (C/2 channels) and pass A reads it in its LayerNorm load stage.
+        import os
+        self.shift_split = os.environ.get("GSN_SHIFT_SPLIT", "1") == "1"
         # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
         self.timeline = None
 
@@ -264,6 +268,15 @@ class Engine:
         a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), partial.data_ptr()
         a.mid_ca = 1 if self.spec.denoise else 0
+        if shift and self.shift_split:
+            ckw = ("wc1", p)
+            if ckw not in self.cache:
+                self.cache[ckw] = self.sd[p + ".conv1.weight"].view(Cc // 2, 9).t().contiguous().half()
+            hw_pre = self._new(T, H, W, Cc // 2)
+            with self._timed("shift_conv1", T * H * W):
+                L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, a.circular, self.cache[ckw].data_ptr(),
+                                                 hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
+            a.hw_pre = hw_pre.data_ptr()
         dbg = None
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
