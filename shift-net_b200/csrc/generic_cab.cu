@@ -10,6 +10,11 @@
 //   cab_fold / cab_pass_b (shift_cab.cu)
 //
 // Same zero-padding rules and the same deterministic per-tile partial sums as the fused path.
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "shift_common.cuh"
 
@@ -250,31 +255,57 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
 // 16x16-pixel tiles, the 34x34x(C/2) source box staged with zero-filling cp.async, per-channel sliding windows,
 // results staged in smem and written with 16-byte stores.  Memory/L2 bound; 2 CTAs per SM overlap load and compute.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool TMA>
 __global__ void __launch_bounds__(256, 2) shift_conv1_kernel(const __half *__restrict__ x, int T, int H, int W, int mode,
                                                              int circular, const __half *__restrict__ wc1,
-                                                             __half *__restrict__ out) {
+                                                             __half *__restrict__ out, const __grid_constant__ CUtensorMap tmap) {
   constexpr int HC = C / 2, CH = HC / 8, TS = 16, BW = TS + 18;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __half *box = reinterpret_cast<__half *>(smem);                       // [BW*BW][HC]
   __half *ot = reinterpret_cast<__half *>(smem + BW * BW * HC * 2);     // [TS*TS][HC]
   const int tid = threadIdx.x;
   const int t = blockIdx.z, x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
   const RollSrc rs = roll_source(mode, circular, t, T, C);
-  const size_t frame = (size_t)H * W * C;
   const bool fwd = mode == GSN_MODE_CAB2_FWD;
-  const __half *src = x + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
-  for (int p = tid; p < BW * BW; p += 256) {
-    const int by = p / BW, bx = p - by * BW;
-    const int gy = y0 - 9 + by, gx = x0 - 9 + bx;
-    const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const __half *sp = valid ? src + ((size_t)gy * W + gx) * C : src;
+  if (TMA) {
+    // One TMA tile load brings the whole 34x34x(C/2) box (out-of-image elements are zero-filled by the hardware).
+    __shared__ __align__(8) unsigned long long bar;
+    const uint32_t bar_s = smem_u32(&bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int c0 = fwd ? rs.c_lo : rs.c_hi, f = fwd ? rs.f_lo : rs.f_hi;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_s), "r"(BW * BW * HC * 2) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+              "r"(smem_u32(box)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(x0 - 9), "r"(y0 - 9), "r"(f), "r"(bar_s)
+          : "memory");
+    }
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done) : "r"(bar_s) : "memory");
+      if (spin > (1 << 24)) __trap();     // a wrong tensor map must not hang the GPU
+    }
+  } else {
+    const size_t frame = (size_t)H * W * C;
+    const __half *src = x + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
+    for (int p = tid; p < BW * BW; p += 256) {
+      const int by = p / BW, bx = p - by * BW;
+      const int gy = y0 - 9 + by, gx = x0 - 9 + bx;
+      const bool valid = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const __half *sp = valid ? src + ((size_t)gy * W + gx) * C : src;
 #pragma unroll
-    for (int ch = 0; ch < CH; ++ch) cp_async16(box + (size_t)p * HC + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+      for (int ch = 0; ch < CH; ++ch) cp_async16(box + (size_t)p * HC + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
   }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
   const bool interior = y0 >= 1 && y0 + TS + 1 <= H && x0 >= 1 && x0 + TS + 1 <= W;   // all destination taps in-image
   for (int item = tid; item < HC * TS; item += 256) {
     const int c = item % HC, oy = item / HC;
@@ -353,11 +384,44 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   if (C != 64) { set_error("shift_conv1: C=%d unsupported (64)", C); return GSN_E_UNSUPPORTED; }
   constexpr int smem = 34 * 34 * 32 * 2 + 16 * 16 * 32 * 2;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(shift_conv1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(shift_conv1_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(shift_conv1_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
   dim3 grid((W + 15) / 16, (H + 15) / 16, T);
-  shift_conv1_kernel<64><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half *>(x), T, H, W, mode, circular, reinterpret_cast<const __half *>(wc1),
-      reinterpret_cast<__half *>(out));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // TMA path: a 4-D tensor map (C, W, H, T) over x with a (C/2, 34, 34, 1) box; GSN_SHIFT_TMA=0 selects the cp.async loader
+  static const bool use_tma = [] { const char *e = getenv("GSN_SHIFT_TMA"); return !(e && e[0] == '0'); }();
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  bool tma_ok = false;
+  if (use_tma && W * (long long)C * 2 % 16 == 0) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = [] {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+      return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (enc) {
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
+      const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)(C / 2), 34, 34, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      tma_ok = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
+  if (tma_ok)
+    shift_conv1_kernel<64, true><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(x), T, H, W, mode, circular,
+                                                          reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(out), tm);
+  else
+    shift_conv1_kernel<64, false><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(x), T, H, W, mode, circular,
+                                                           reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(out), tm);
   count_launch();
   return check_launch("shift_conv1");
 }
