@@ -171,7 +171,7 @@ int gsn_cab_pass_b(const GsnCabPassB *d, void *stream);
 /* [roll + shift gather + conv1] + LayerNorm -> out (T,H,W,cinp) fp16, cinp = pad16(C or 3C/2), padding channels 0.
  * wc1: fp16 [9][C/2] (CAB2 modes); ln: fp32 gamma[cin] then beta[cin]. */
 int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
-                 void *out, int cinp, void *stream);
+                 void *out, int cinp, const void *hw_pre /* optional (T,H,W,C/2) from gsn_shift_conv1 */, void *stream);
 /* g = (dw3x3(a)+a) * (dw3x3(b)+b) (RepConv2 + SimpleGate); wd fp16 [9][2C]; partial (optional) [T][tiles_linear][C]. */
 int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,
                 void *stream);

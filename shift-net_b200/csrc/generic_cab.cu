@@ -32,7 +32,8 @@ __device__ __forceinline__ void shift_offset_rt(int C, int c, int &dy, int &dx) 
 __global__ void __launch_bounds__(256) shift_ln_kernel(const __half *__restrict__ x, int T, int H, int W, int C, int mode,
                                                        int circular, const __half *__restrict__ wc1 /*[9][C/2]*/,
                                                        const float *__restrict__ ln /*gamma[CIN], beta[CIN]*/,
-                                                       __half *__restrict__ out, int cinp) {
+                                                       __half *__restrict__ out, int cinp,
+                                                       const __half *__restrict__ hw_pre /*(T,H,W,C/2) or null*/) {
   const int lane16 = threadIdx.x & 15;
   const long long hw = (long long)H * W;
   const long long pix = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
@@ -55,6 +56,8 @@ __global__ void __launch_bounds__(256) shift_ln_kernel(const __half *__restrict_
       unpack8(__ldg(reinterpret_cast<const uint4 *>(x + rs.f_lo * frame + (size_t)pix * C + rs.c_lo + cb)), v);
     } else if (cb < C) {
       unpack8(__ldg(reinterpret_cast<const uint4 *>(x + rs.f_hi * frame + (size_t)pix * C + rs.c_hi + cb - HC)), v);
+    } else if (hw_pre) {
+      unpack8(__ldg(reinterpret_cast<const uint4 *>(hw_pre + ((size_t)t * hw + pix) * HC + cb - C)), v);
     } else {
       // shifted half: neighbour frame's channels, per-channel (dy,dx), zero fill, then dw3x3 with zero padding
       const bool fwd = mode == GSN_MODE_CAB2_FWD;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
 // results staged in smem and written with 16-byte stores.  Memory/L2 bound; 2 CTAs per SM overlap load and compute.
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, bool TMA>
-__global__ void __launch_bounds__(256, 2) shift_conv1_kernel(const __half *__restrict__ x, int T, int H, int W, int mode,
+__global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(const __half *__restrict__ x, int T, int H, int W, int mode,
                                                              int circular, const __half *__restrict__ wc1,
                                                              __half *__restrict__ out, const __grid_constant__ CUtensorMap tmap) {
   constexpr int HC = C / 2, CH = HC / 8, TS = 16, BW = TS + 18;
@@ -381,12 +384,14 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   GSN_REQUIRE(x && wc1 && out, "shift_conv1: null pointer");
   GSN_REQUIRE(T > 0 && H > 0 && W > 0, "shift_conv1: empty shape");
   GSN_REQUIRE(mode == GSN_MODE_CAB2_FWD || mode == GSN_MODE_CAB2_REV, "shift_conv1: mode=%d is not a shift mode", mode);
-  if (C != 64) { set_error("shift_conv1: C=%d unsupported (64)", C); return GSN_E_UNSUPPORTED; }
-  constexpr int smem = 34 * 34 * 32 * 2 + 16 * 16 * 32 * 2;
+  if (C != 64 && C != 80) { set_error("shift_conv1: C=%d unsupported (64, 80)", C); return GSN_E_UNSUPPORTED; }
+  const int smem = (34 * 34 + 16 * 16) * (C / 2) * 2;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(shift_conv1_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(shift_conv1_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(shift_conv1_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 32 * 2);
+    cudaFuncSetAttribute(shift_conv1_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 32 * 2);
+    cudaFuncSetAttribute(shift_conv1_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 40 * 2);
+    cudaFuncSetAttribute(shift_conv1_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 40 * 2);
     attr = true;
   }
   dim3 grid((W + 15) / 16, (H + 15) / 16, T);
@@ -416,27 +421,30 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
   }
-  if (tma_ok)
-    shift_conv1_kernel<64, true><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(x), T, H, W, mode, circular,
-                                                          reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(out), tm);
-  else
-    shift_conv1_kernel<64, false><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(x), T, H, W, mode, circular,
-                                                           reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(out), tm);
+  const __half *xh = reinterpret_cast<const __half *>(x), *wh = reinterpret_cast<const __half *>(wc1);
+  __half *oh = reinterpret_cast<__half *>(out);
+  if (C == 64) {
+    if (tma_ok) shift_conv1_kernel<64, true><<<grid, 256, smem, st>>>(xh, T, H, W, mode, circular, wh, oh, tm);
+    else shift_conv1_kernel<64, false><<<grid, 256, smem, st>>>(xh, T, H, W, mode, circular, wh, oh, tm);
+  } else {
+    if (tma_ok) shift_conv1_kernel<80, true><<<grid, 256, smem, st>>>(xh, T, H, W, mode, circular, wh, oh, tm);
+    else shift_conv1_kernel<80, false><<<grid, 256, smem, st>>>(xh, T, H, W, mode, circular, wh, oh, tm);
+  }
   count_launch();
   return check_launch("shift_conv1");
 }
 
 extern "C" int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
-                            void *out, int cinp, void *stream) {
+                            void *out, int cinp, const void *hw_pre, void *stream) {
   using namespace gsn;
   GSN_REQUIRE(x && ln && out, "shift_ln: null pointer");
   GSN_REQUIRE(C % 16 == 0 && C <= 80 && cinp % 8 == 0 && cinp <= 128 && T > 0 && H > 0 && W > 0, "shift_ln: bad sizes C=%d cinp=%d", C, cinp);
-  GSN_REQUIRE(mode == GSN_MODE_CAB1 || wc1, "shift_ln: conv1 weights missing");
+  GSN_REQUIRE(mode == GSN_MODE_CAB1 || wc1 || hw_pre, "shift_ln: conv1 weights missing");
   const long long hw = (long long)H * W;
   dim3 grid((unsigned)((hw + 15) / 16), T);
   shift_ln_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half *>(x), T, H, W, C, mode, circular, reinterpret_cast<const __half *>(wc1), ln,
-      reinterpret_cast<__half *>(out), cinp);
+      reinterpret_cast<__half *>(out), cinp, reinterpret_cast<const __half *>(hw_pre));
   count_launch();
   return check_launch("shift_ln");
 }

@@ -217,10 +217,16 @@ class Engine:
         cin = Cc + Cc // 2 if shift else Cc
         cinp = P.pad16(cin)
         a1 = self._new(T, H, W, cinp)
+        hw_pre = None
+        if shift:      # gather folded into conv1's load stage (TMA-staged box), written once, read by the LayerNorm kernel
+            hw_pre = self._new(T, H, W, Cc // 2)
+            with self._timed("shift_conv1", T * H * W):
+                L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0, wc1.data_ptr(),
+                                                 hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
         with self._timed("shift_ln", T * H * W):
             L.check(self.lib.gsn_shift_ln(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0,
                                           wc1.data_ptr() if wc1 is not None else None, ln.data_ptr(), a1.data_ptr(), cinp,
-                                          self._stream()), "shift_ln " + p)
+                                          hw_pre.data_ptr() if hw_pre is not None else None, self._stream()), "shift_ln " + p)
         ga = self.conv(p + ".body.0#a", [a1], [cin], Cc)
         gb = self.conv(p + ".body.0#b", [a1], [cin], Cc)
         ntl = self.lib.gsn_cab_tiles_linear(H * W)
