@@ -11,7 +11,7 @@
  *   - every pointer is a raw DEVICE pointer (cudaMalloc'd / torch storage); nothing is owned or
  *     freed by the library; all calls are stream-ordered and stateless (thread-safe per stream);
  *   - activations are NHWC fp16, shape (T, H, W, Cp) with Cp = channel count padded to a multiple
- *     of 16 (padding channels are zero and stay zero);
+ *     of 8 (one 16-byte vector; padding channels are zero and stay zero);
  *   - return value: 0 on success, negative GSN_E_* on failure; gsn_last_error() gives the message
  *     of the last failure on the calling thread;
  *   - ``stream`` is a cudaStream_t passed as void*.
@@ -50,9 +50,9 @@ typedef struct {
   int T, Hin, Win, Hout, Wout;
   int n_src;            /* 1..3 sources, concatenated along channels */
   const void *src[3];   /* NHWC fp16 (T,Hin,Win,src_c[i]) */
-  int src_c[3];         /* padded channel count of each source (multiple of 8) */
-  int cin_p;            /* sum of src_c, multiple of 16 */
-  int cout_p;           /* padded output channels: 16, 32, 48, 64, 80 or 96 */
+  int src_c[3];         /* stored channel count of each source (multiple of 8) */
+  int cin_p;            /* GEMM K: sum of src_c rounded up to 16 (the tail is zero-filled in shared memory only) */
+  int cout_p;           /* stored output channels: 16, 24, 32, 40, 48, 64, 80 or 96 */
   int ks, stride, pad;  /* kernel size 1..3, stride 1..2, zero padding */
   const void *wpack;    /* fp16 weights in mma.m16n8k16 B-fragment order: [tap][cin_p/16][cout_p/8][32 lanes][4] */
   const float *bias;    /* cout_p floats or NULL */

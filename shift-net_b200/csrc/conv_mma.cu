@@ -34,18 +34,19 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
     const int chunks = cin_p >> 3;
     if (d.n_src == 1) {
       const __half *base = reinterpret_cast<const __half *>(d.src[0]);
+      const int stored = d.src_c[0], schunks = stored >> 3;   // stored width may be 8 short of the K slot (e.g. 24 of 32)
       for (int px = tid; px < IH * IW; px += 256) {
         const int ly = px / IW, lx = px - ly * IW;
         const int gy = iy0 + ly, gx = ix0 + lx;
         const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
-        const __half *sp = valid ? base + (((size_t)t * d.Hin + gy) * d.Win + gx) * cin_p : base;
+        const __half *sp = valid ? base + (((size_t)t * d.Hin + gy) * d.Win + gx) * stored : base;
         __half *dp = tile + (size_t)px * pitch;
 #pragma unroll
         for (int ch = 0; ch < (CINP ? CINP / 8 : 1); ++ch) {
-          if (CINP) cp_async16(dp + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+          if (CINP) { const bool v = valid && ch < schunks; cp_async16(dp + ch * 8, sp + (v ? ch * 8 : 0), v); }
         }
         if (!CINP)
-          for (int ch = 0; ch < chunks; ++ch) cp_async16(dp + ch * 8, sp + (valid ? ch * 8 : 0), valid);
+          for (int ch = 0; ch < chunks; ++ch) { const bool v = valid && ch < schunks; cp_async16(dp + ch * 8, sp + (v ? ch * 8 : 0), v); }
       }
     } else {
       const int c1 = d.src_c[0], c2 = d.src_c[0] + d.src_c[1];
@@ -55,13 +56,15 @@ __global__ void __launch_bounds__(256, (NT <= 4 ? 4 : 2)) conv_mma_kernel(const 
         const bool valid = (gy >= 0) && (gy < d.Hin) && (gx >= 0) && (gx < d.Win);
         const size_t gpix = valid ? ((size_t)t * d.Hin + gy) * d.Win + gx : 0;
         __half *dp = tile + (size_t)px * pitch;
+        const int stored = c2 + (d.n_src > 2 ? d.src_c[2] : 0);
         for (int ch = 0; ch < chunks; ++ch) {
           const int c = ch * 8;
           int s = 0, cb = 0;
           if (c >= c2 && d.n_src > 2) { s = 2; cb = c2; }
           else if (c >= c1) { s = 1; cb = c1; }
           const __half *base = reinterpret_cast<const __half *>(d.src[s]);
-          cp_async16(dp + c, valid ? base + gpix * d.src_c[s] + (c - cb) : base, valid);
+          const bool v = valid && c < stored;
+          cp_async16(dp + c, v ? base + gpix * d.src_c[s] + (c - cb) : base, v);
         }
       }
     }
@@ -228,6 +231,8 @@ static int launch_conv_nt(const GsnConvDesc &d, cudaStream_t st) {
   // specialised (fully unrolled) instances for the layer shapes of the four nets
 #define GSN_CONV_CASE(CIN, K, S) if (key == CIN * 100 + K * 10 + S) return launch_conv<NT, K, S, CIN>(d, st);
   if constexpr (NT == 2) { GSN_CONV_CASE(16, 3, 1) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 1) }
+  if constexpr (NT == 3) { GSN_CONV_CASE(32, 3, 1) GSN_CONV_CASE(16, 3, 2) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 1, 1) GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(96, 3, 1) }
+  if constexpr (NT == 5) { GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(48, 1, 1) }
   if constexpr (NT == 4) { GSN_CONV_CASE(32, 3, 1) GSN_CONV_CASE(16, 3, 2) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(32, 1, 1) GSN_CONV_CASE(48, 1, 1) GSN_CONV_CASE(96, 3, 1) GSN_CONV_CASE(64, 3, 1) }
   if constexpr (NT == 6) { GSN_CONV_CASE(48, 3, 1) GSN_CONV_CASE(32, 3, 2) GSN_CONV_CASE(48, 3, 2) GSN_CONV_CASE(48, 1, 1) }
   if constexpr (NT == 8) { GSN_CONV_CASE(64, 3, 1) GSN_CONV_CASE(64, 3, 2) GSN_CONV_CASE(64, 1, 1) GSN_CONV_CASE(16, 2, 2) }
@@ -256,7 +261,7 @@ extern "C" int gsn_conv_mma(const GsnConvDesc *dp, void *stream) {
     GSN_REQUIRE(d.src[i] && d.src_c[i] > 0 && d.src_c[i] % 8 == 0, "conv_mma: bad source %d (c=%d)", i, d.src_c[i]);
     csum += d.src_c[i];
   }
-  GSN_REQUIRE(csum == d.cin_p && d.cin_p % 16 == 0, "conv_mma: cin_p=%d must be the sum of sources (%d) and %%16", d.cin_p, csum);
+  GSN_REQUIRE(d.cin_p == (csum + 15) / 16 * 16, "conv_mma: cin_p=%d must be the sum of the sources (%d) rounded up to 16", d.cin_p, csum);
   GSN_REQUIRE(d.ks >= 1 && d.ks <= 3 && d.stride >= 1 && d.stride <= 2, "conv_mma: ks=%d stride=%d unsupported", d.ks, d.stride);
   GSN_REQUIRE(d.T > 0 && d.Hin > 0 && d.Win > 0 && d.Hout > 0 && d.Wout > 0, "conv_mma: empty shape");
   GSN_REQUIRE((d.Hin + 2 * d.pad - d.ks) / d.stride + 1 == d.Hout && (d.Win + 2 * d.pad - d.ks) / d.stride + 1 == d.Wout,
@@ -267,11 +272,13 @@ extern "C" int gsn_conv_mma(const GsnConvDesc *dp, void *stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (d.cout_p) {
     case 16: return launch_conv_nt<2>(d, st);
+    case 24: return launch_conv_nt<3>(d, st);
+    case 40: return launch_conv_nt<5>(d, st);
     case 32: return launch_conv_nt<4>(d, st);
     case 48: return launch_conv_nt<6>(d, st);
     case 64: return launch_conv_nt<8>(d, st);
     case 80: return launch_conv_nt<10>(d, st);
     case 96: return launch_conv_nt<12>(d, st);
-    default: set_error("conv_mma: cout_p=%d unsupported (16/32/48/64/80/96)", d.cout_p); return GSN_E_UNSUPPORTED;
+    default: set_error("conv_mma: cout_p=%d unsupported (16/24/32/40/48/64/80/96)", d.cout_p); return GSN_E_UNSUPPORTED;
   }
 }

@@ -114,6 +114,10 @@ extern "C" int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, in
     conv_in_kernel<__half, 16><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
   else if (cout_p == 16 && x_dtype == GSN_DTYPE_F32)
     conv_in_kernel<float, 16><<<grid, block, 0, st>>>((const float *)x, T, cin, H, W, w, bias, d);
+  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F16)
+    conv_in_kernel<__half, 24><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
+  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F32)
+    conv_in_kernel<float, 24><<<grid, block, 0, st>>>((const float *)x, T, cin, H, W, w, bias, d);
   else if (cout_p == 32 && x_dtype == GSN_DTYPE_F16)
     conv_in_kernel<__half, 32><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
   else if (cout_p == 32 && x_dtype == GSN_DTYPE_F32)
@@ -141,12 +145,16 @@ extern "C" int gsn_conv_out(const void *src, int cp, int ks, const float *w, con
     else if (cp == 16 && ks == 3) GSN_CO(__half, 16, 3);
     else if (cp == 32 && ks == 5) GSN_CO(__half, 32, 5);
     else if (cp == 32 && ks == 3) GSN_CO(__half, 32, 3);
+    else if (cp == 24 && ks == 5) GSN_CO(__half, 24, 5);
+    else if (cp == 24 && ks == 3) GSN_CO(__half, 24, 3);
     else { set_error("conv_out: cp=%d ks=%d unsupported", cp, ks); return GSN_E_UNSUPPORTED; }
   } else if (x_dtype == GSN_DTYPE_F32) {
     if (cp == 16 && ks == 5) GSN_CO(float, 16, 5);
     else if (cp == 16 && ks == 3) GSN_CO(float, 16, 3);
     else if (cp == 32 && ks == 5) GSN_CO(float, 32, 5);
     else if (cp == 32 && ks == 3) GSN_CO(float, 32, 3);
+    else if (cp == 24 && ks == 5) GSN_CO(float, 24, 5);
+    else if (cp == 24 && ks == 3) GSN_CO(float, 24, 3);
     else { set_error("conv_out: cp=%d ks=%d unsupported", cp, ks); return GSN_E_UNSUPPORTED; }
   } else {
     set_error("conv_out: dtype=%d unsupported", x_dtype);

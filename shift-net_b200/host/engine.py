@@ -77,7 +77,7 @@ class Engine:
         T, Hin, Win = srcs[0].shape[:3]
         Hout = (Hin + 2 * pad - ks) // stride + 1
         Wout = (Win + 2 * pad - ks) // stride + 1
-        cout_p = P.pad16(cout)
+        cout_p = P.pad16(cout) if pixel_shuffle else P.pad8(cout)   # shuffle: 4 conv channels per output channel
         src_pad = [s.shape[3] for s in srcs]
         ck = ("conv", key)
         if ck not in self.cache:
@@ -87,7 +87,7 @@ class Engine:
         wp, bias = self.cache[ck]
         dst_c = 0
         if pixel_shuffle:
-            dst_c = P.pad16(cout // 4)
+            dst_c = P.pad8(cout // 4)
             if dst_c == cout_p // 4:
                 dst = self._new(T, 2 * Hout, 2 * Wout, dst_c)
             else:                                   # padding channels are never written by the shuffle store
@@ -104,7 +104,7 @@ class Engine:
             assert s.is_contiguous() and s.dtype == torch.float16
             d.src[i] = s.data_ptr()
             d.src_c[i] = s.shape[3]
-        d.cin_p, d.cout_p, d.ks, d.stride, d.pad = sum(src_pad), cout_p, ks, stride, pad
+        d.cin_p, d.cout_p, d.ks, d.stride, d.pad = P.pad16(sum(src_pad)), cout_p, ks, stride, pad
         d.wpack = wp.data_ptr()
         d.bias = bias.data_ptr() if bias is not None else None
         d.has_prelu = 1 if prelu_key else 0
@@ -397,7 +397,7 @@ class Engine:
             raise ValueError("clip too short for the requested past/future context")
         dt = L.DTYPE_F16 if xin.dtype == torch.float16 else L.DTYPE_F32
         n0 = sp.n0
-        n0p = P.pad16(n0)
+        n0p = P.pad8(n0)
         if "in" not in self.cache:
             self.cache["in"] = P.pack_conv_in(self.sd["feat_extract.0.weight"], self.sd["feat_extract.0.bias"], n0p)
             self.cache["out"] = P.pack_conv_out(self.sd["conv_last.weight"], n0p)

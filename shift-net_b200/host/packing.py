@@ -11,6 +11,11 @@ def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
+def pad8(c: int) -> int:
+    """Storage width of an activation tensor: channels padded to one 16-byte vector (8 fp16)."""
+    return (c + 7) // 8 * 8
+
+
 def pack_conv_mma(w: torch.Tensor, src_real, src_pad, cout_p: int) -> torch.Tensor:
     """Dense conv weight (cout, sum(src_real), k, k) -> fp16 [tap][cin_p/16][cout_p/8][32 lanes][4]
     (mma.m16n8k16 B fragments; csrc/conv_mma.cu).  Each source's real channels are placed at the start of
@@ -18,8 +23,8 @@ def pack_conv_mma(w: torch.Tensor, src_real, src_pad, cout_p: int) -> torch.Tens
     w = w.float()
     cout, cin, k, _ = w.shape
     assert cin == sum(src_real)
-    cin_p = sum(src_pad)
-    assert cin_p % 16 == 0 and cout_p % 8 == 0 and cout <= cout_p
+    cin_p = pad16(sum(src_pad))      # the GEMM K dimension is padded to the mma k-step in shared memory only
+    assert cout_p % 8 == 0 and cout <= cout_p and all(p % 8 == 0 for p in src_pad)
     wp = torch.zeros(cout_p, cin_p, k * k, device=w.device)
     ro = po = 0
     for r, p in zip(src_real, src_pad):

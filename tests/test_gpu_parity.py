@@ -24,7 +24,7 @@ DEV = "cuda:0"
 def to_nhwc(x, cp=None):
     """(T,C,H,W) fp32 cpu -> (T,H,W,Cp) fp16 cuda, zero padded channels."""
     T, C, H, W = x.shape
-    cp = cp or (C + 15) // 16 * 16
+    cp = cp or (C + 7) // 8 * 8          # storage convention: channels padded to one 16-byte vector
     out = torch.zeros(T, H, W, cp, dtype=torch.float16, device=DEV)
     out[..., :C] = x.permute(0, 2, 3, 1).to(DEV).half()
     return out
@@ -145,9 +145,9 @@ def test_upsample_add(env):
     g = torch.Generator().manual_seed(8)
     x = torch.randn(2, 18, 10, 14, generator=g)
     skip = torch.randn(2, 18, 20, 28, generator=g)
-    out = torch.empty(2, 20, 28, 32, dtype=torch.float16, device=DEV)
-    xd, sk = to_nhwc(x), to_nhwc(skip)      # keep the device tensors alive across the async launch
-    gio.pkg("host.lib").check(eng.lib.gsn_upsample2x_add(xd.data_ptr(), sk.data_ptr(), out.data_ptr(), 2, 10, 14, 32, eng._stream()))
+    out = torch.empty(2, 20, 28, 24, dtype=torch.float16, device=DEV)
+    xd, sk = to_nhwc(x), to_nhwc(skip)      # keep the device tensors alive across the async launch (18 -> 24 channels)
+    gio.pkg("host.lib").check(eng.lib.gsn_upsample2x_add(xd.data_ptr(), sk.data_ptr(), out.data_ptr(), 2, 10, 14, 24, eng._stream()))
     torch.cuda.synchronize()
     ref = F.interpolate(x.half().float(), scale_factor=2, mode="bilinear", align_corners=False) + skip.half().float()
     check(from_nhwc(out, 18), ref, 1e-3, "upsample2x_add")
