@@ -18,7 +18,9 @@ T, H, W = 20, 360, 640
 x = (0.5 * torch.randn(T, H, W, 64, device="cuda")).half()
 names = {True: ["start", "loads", "gather", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"],
          False: ["start", "loads", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]}
-for p, mode in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD), ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1)):
+for p, mode, split in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, False),
+                       ("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True),
+                       ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1, False)):
     shift = mode != L.MODE_CAB1
     blob = gio.pkg("host.packing").pack_cab_pass_a(eng.sd, p, 64, shift, 0)
     nt = eng.lib.gsn_cab_tiles(mode, H, W)
@@ -29,13 +31,19 @@ for p, mode in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD), ("s
     a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, 64, mode, 1
     a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), part.data_ptr()
     a.debug_stage, a.debug_out = 9, dbg.data_ptr()
+    if split:
+        wc1 = eng.sd[p + ".conv1.weight"].view(32, 9).t().contiguous().half()
+        hw_pre = torch.empty(T, H, W, 32, dtype=torch.float16, device="cuda")
+        L.check(eng.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, 64, mode, 1, wc1.data_ptr(), hw_pre.data_ptr(), eng._stream()))
+        a.hw_pre = hw_pre.data_ptr()
     for _ in range(2):
         L.check(eng.lib.gsn_cab_pass_a(C.byref(a), eng._stream()))
     torch.cuda.synchronize()
     c = dbg.view(T * nt, 16).double()
-    n = len(names[shift])
+    nm = names[shift and not split]
+    n = len(nm)
     d = (c[:, 1:n] - c[:, :n - 1])
     tot = (c[:, n - 1] - c[:, 0])
-    print(f"mode={'shift' if shift else 'cab1'} tiles={T*nt} mean cycles/tile={tot.mean().item():.0f} (min {tot.min().item():.0f} max {tot.max().item():.0f})")
+    print(f"mode={'shift' if shift else 'cab1'} split={split} tiles={T*nt} mean cycles/tile={tot.mean().item():.0f} (min {tot.min().item():.0f} max {tot.max().item():.0f})")
     for i in range(n - 1):
-        print(f"   {names[shift][i+1]:12s} {d[:, i].mean().item():8.0f}  ({100 * d[:, i].mean().item() / tot.mean().item():4.1f}%)")
+        print(f"   {nm[i+1]:12s} {d[:, i].mean().item():8.0f}  ({100 * d[:, i].mean().item() / tot.mean().item():4.1f}%)")

@@ -10,6 +10,9 @@
 //
 // Reference semantics: gshift_deblur2.py:186-258 (CAB1/CAB2), :465-519 (spatial_shift2 / channel_shift).
 // Stage order and zero-padding rules are identical to the mma.sync version in shift_cab.cu (kept as a cross-check).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "shift_common.cuh"
 
@@ -23,7 +26,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+  int spin = 0;
   do {
+    if (++spin > (1 << 26)) __trap();   // a lost TMA / MMA completion must fault, not hang the GPU
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -120,7 +125,9 @@ __device__ __forceinline__ void h8_mul(H8 &acc, const H8 &a, const H8 &w) {
 // ---- configuration ----------------------------------------------------------------------------------
 // SHIFT: CAB2 (LayerNorm input = [rolled stream | conv1(shifted half)]).  BOX: the gather runs inside this kernel (bounding
 // box staged in smem); SHIFT && !BOX: the shifted+conv1'd half was produced by shift_conv1_kernel and is read from HBM.
-template <int C, bool SHIFT, bool BOX = SHIFT>
+// TMAIN: the LayerNorm inputs of the tile (22x22 halo'd region) are staged in shared memory by TMA tile loads
+// (hardware zero fill outside the image) instead of per-lane global loads.
+template <int C, bool SHIFT, bool BOX = SHIFT, bool TMAIN = false>
 struct TcCfg {
   static constexpr int TW = 16, TH = 16;
   static constexpr int HC = C / 2;
@@ -162,20 +169,25 @@ struct TcCfg {
   static constexpr int GT_BYTES = KC2 * P2;
   static constexpr int S_WT2 = (S_GT + GT_BYTES + 127) / 128 * 128;
   static constexpr int END2 = S_WT2 + WT2_BYTES;
-  static constexpr int END1 = S_R + R12_BYTES;
+  static constexpr int IN_BYTES = TMAIN ? (SHIFT ? 3 * M1 * HC * 2 : M1 * C * 2) : 0;    // TMA staging of the LN inputs
+  static constexpr int END1 = S_R + (R12_BYTES > IN_BYTES ? R12_BYTES : IN_BYTES);
+  static constexpr bool LATE_WT2 = BOX || TMAIN;   // phase-2 weights go where the box / staging lived: load them later
   static constexpr int SMEM = END1 > END2 ? END1 : END2;
   static constexpr int S_A2 = S_G1;                                  // GEMM2 operand, then the z staging tile
   static_assert(2 * CIN * 4 <= 1024 && 9 * HC * 2 <= 704, "X region layout");
   static_assert(KC2 * P3 <= G1_BYTES, "A2 aliases G1");
-  static_assert(!BOX || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box, not over A1/W1");
-  static_assert(BOX || S_WT2 >= S_A1 + A1_BYTES, "WT2 must not overlap A1 while GEMM1 reads it");
+  static_assert(!LATE_WT2 || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box / staging, not over A1/W1");
+  static_assert(LATE_WT2 || S_WT2 >= S_A1 + A1_BYTES, "WT2 must not overlap A1 while GEMM1 reads it");
+  static_assert(!(BOX && TMAIN), "the in-kernel gather variant keeps its cp.async loaders");
   static_assert(S_A1 + (KC1 - 1) * P1 + (MT1 * 128) * 16 <= SMEM, "UMMA rows beyond M1 must stay inside the allocation");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int C, bool SHIFT, bool MIDCA, bool BOX>
-__global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnCabPassA d, const ShiftTable tab) {
-  using K = TcCfg<C, SHIFT, BOX>;
+template <int C, bool SHIFT, bool MIDCA, bool BOX, bool TMAIN>
+__global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnCabPassA d, const ShiftTable tab,
+                                                                      const __grid_constant__ CUtensorMap tm_x,
+                                                                      const __grid_constant__ CUtensorMap tm_hw) {
+  using K = TcCfg<C, SHIFT, BOX, TMAIN>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.z, x0 = blockIdx.x * K::TW, y0 = blockIdx.y * K::TH;
@@ -193,8 +205,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   GSN_CLK();
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + K::S_X + K::X_TMEM);
 
-  // ---- P0: async loads (small params, W1, gather box), TMEM allocation, barrier init ---------------
+  // ---- P0: async loads (small params, W1, gather box / TMA staging), TMEM allocation, barrier init ---------------
+  const uint32_t bar_in = bar + 8;
   {
+    if (tid == 32) {
+      mbar_init(bar, 1);
+      mbar_init(bar_in, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (TMAIN && tid == 0) {
+      // LN inputs of the whole 22x22 region: one (CAB1) or three (CAB2: rolled low half, rolled high half, shifted half)
+      // TMA tile loads; pixels outside the image arrive as zeros.
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_in), "r"(K::IN_BYTES) : "memory");
+      const uint32_t dst = smem_u32(smem + K::S_R);
+      auto tma4 = [&](uint32_t sdst, const CUtensorMap *tm, int c0, int f) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+                "r"(sdst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(x0 - 3), "r"(y0 - 3), "r"(f), "r"(bar_in)
+            : "memory");
+      };
+      if (SHIFT) {
+        tma4(dst, &tm_x, rs.c_lo, rs.f_lo);
+        tma4(dst + K::M1 * K::HC * 2, &tm_x, rs.c_hi, rs.f_hi);
+        tma4(dst + 2 * K::M1 * K::HC * 2, &tm_hw, 0, t);
+      } else {
+        tma4(dst, &tm_x, 0, t);
+      }
+    }
     for (int i = tid; i < (K::OFF_W1 - K::OFF_LN) / 16; i += kTcThreads) {  // LN params (+ conv1 weights)
       const int off = i * 16;
       unsigned char *dst = (off < K::OFF_C1) ? smem + K::S_X + K::X_LN + off : smem + K::S_X + K::X_C1 + (off - K::OFF_C1);
@@ -214,17 +252,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) cp_async16(dp + ch * 16, sp + (valid ? ch * 8 : 0), valid);
       }
-    } else {
+    } else if (!K::LATE_WT2) {
       for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
     }
     cp_async_commit();
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
-    }
-    if (tid == 32) {
-      mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     cp_async_wait<0>();
     tc_fence_before();
@@ -332,6 +366,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     for (int k = 0; k < NV / 8; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { gam[k * 8 + i] = ln_g[chunk_of[k] * 8 + i]; bet[k * 8 + i] = ln_b[chunk_of[k] * 8 + i]; }
+    if (TMAIN) mbar_wait(bar_in, 0);                 // the staged LN inputs have landed
+    const unsigned char *stg = smem + K::S_R;
     constexpr int PB = (SHIFT && !BOX) ? 2 : NIT;    // items whose loads are in flight together (register budget)
 #pragma unroll
     for (int it0 = 0; it0 < NIT; it0 += PB) {
@@ -344,7 +380,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
       raw[it][0] = raw[it][1] = make_uint4(0, 0, 0, 0);
       if (SHIFT && !BOX) raw[it][(SHIFT && !BOX) ? 2 : 0] = make_uint4(0, 0, 0, 0);
-      if (inimg) {
+      if (TMAIN) {
+        if (q < K::M1) {
+          if (SHIFT) {
+            raw[it][0] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * K::HC * 2 + j * 16);
+            raw[it][1] = *reinterpret_cast<const uint4 *>(stg + K::M1 * K::HC * 2 + (size_t)q * K::HC * 2 + j * 16);
+            raw[it][(SHIFT && !BOX) ? 2 : 0] = *reinterpret_cast<const uint4 *>(stg + 2 * K::M1 * K::HC * 2 + (size_t)q * K::HC * 2 + j * 16);
+          } else {
+            raw[it][0] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + j * 32);
+            raw[it][1] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + j * 32 + 16);
+          }
+        }
+      } else if (inimg) {
         const size_t pix = ((size_t)gy * d.W + gx) * C;
         if (SHIFT) {
           raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8));
@@ -406,6 +453,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
     __syncthreads();
     GSN_CLK();  // LN done
+    if (TMAIN) {           // the staging area is dead: stream the phase-2 weights (dw taps + W2) into its place
+      for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
+      cp_async_commit();
+    }
   }
   if (d.debug_stage == 1) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
@@ -430,7 +481,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     umma_commit(bar);
   }
-  if (BOX) cp_async_wait<0>();     // phase-2 weights landed (issued after the gather)
+  if (K::LATE_WT2) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather / the LayerNorm)
   mbar_wait(bar, 0);
   tc_fence_after();
   __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
@@ -716,33 +767,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
 }
 
-template <int C, bool SHIFT, bool MIDCA, bool BOX>
-static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st) {
-  using K = TcCfg<C, SHIFT, BOX>;
+template <int C, bool SHIFT, bool MIDCA, bool BOX, bool TMAIN>
+static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st, const CUtensorMap &tm_x, const CUtensorMap &tm_hw) {
+  using K = TcCfg<C, SHIFT, BOX, TMAIN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaFuncSetAttribute(cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX, TMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     attr_set = true;
   }
   static const ShiftTable tab = make_shift_table(C);
   dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + K::TH - 1) / K::TH, d.T);
-  cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX><<<grid, kTcThreads, K::SMEM, st>>>(d, tab);
+  cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX, TMAIN><<<grid, kTcThreads, K::SMEM, st>>>(d, tab, tm_x, tm_hw);
   count_launch();
   return check_launch("cab_pass_a_tc");
 }
 
+template <int C, bool SHIFT, bool BOX, bool TMAIN>
+static int launch_pass_a_mid(const GsnCabPassA &d, cudaStream_t st, const CUtensorMap &tm_x, const CUtensorMap &tm_hw) {
+  return d.mid_ca ? launch_pass_a_tc<C, SHIFT, true, BOX, TMAIN>(d, st, tm_x, tm_hw)
+                  : launch_pass_a_tc<C, SHIFT, false, BOX, TMAIN>(d, st, tm_x, tm_hw);
+}
+
 int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st) {
-  if (d.C == 64) {
-    const bool split = d.hw_pre != nullptr;      // shifted half precomputed by gsn_shift_conv1
-    if (d.mid_ca) {
-      if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, true, false>(d, st);
-      return split ? launch_pass_a_tc<64, true, true, false>(d, st) : launch_pass_a_tc<64, true, true, true>(d, st);
-    }
-    if (d.mode == GSN_MODE_CAB1) return launch_pass_a_tc<64, false, false, false>(d, st);
-    return split ? launch_pass_a_tc<64, true, false, false>(d, st) : launch_pass_a_tc<64, true, false, true>(d, st);
+  if (d.C != 64) {
+    set_error("cab_pass_a: C=%d unsupported by the fused kernel (64)", d.C);
+    return GSN_E_UNSUPPORTED;
   }
-  set_error("cab_pass_a: C=%d unsupported (64)", d.C);
-  return GSN_E_UNSUPPORTED;
+  constexpr int C = 64;
+  static const bool want_tma = [] { const char *e = getenv("GSN_PASS_A_TMA"); return !(e && e[0] == '0'); }();
+  CUtensorMap tm_x, tm_hw;
+  memset(&tm_x, 0, sizeof(tm_x));
+  memset(&tm_hw, 0, sizeof(tm_hw));
+  const bool shift = d.mode != GSN_MODE_CAB1;
+  const bool split = shift && d.hw_pre != nullptr;      // shifted half precomputed by gsn_shift_conv1
+  bool tma = want_tma && (!shift || split);
+  if (tma) tma = encode_tmap_nhwc(&tm_x, d.x, C, d.W, d.H, d.T, shift ? C / 2 : C, 22, 22);
+  if (tma && split) tma = encode_tmap_nhwc(&tm_hw, d.hw_pre, C / 2, d.W, d.H, d.T, C / 2, 22, 22);
+  if (!shift) return tma ? launch_pass_a_mid<C, false, false, true>(d, st, tm_x, tm_hw) : launch_pass_a_mid<C, false, false, false>(d, st, tm_x, tm_hw);
+  if (!split) return launch_pass_a_mid<C, true, true, false>(d, st, tm_x, tm_hw);
+  return tma ? launch_pass_a_mid<C, true, false, true>(d, st, tm_x, tm_hw) : launch_pass_a_mid<C, true, false, false>(d, st, tm_x, tm_hw);
 }
 
 }  // namespace gsn

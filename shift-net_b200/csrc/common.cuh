@@ -1,5 +1,6 @@
 // Shared device/host helpers for the shiftnet_b200 kernels (sm_100a).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,6 +14,8 @@ namespace gsn {
 void set_error(const char *fmt, ...);
 void count_launch();
 int check_launch(const char *what);   // cudaGetLastError -> GSN_E_CUDA + message
+// 4-D fp16 NHWC tensor map (dims innermost first: C, W, H, T) with a (bc, bw, bh, 1) box, zero OOB fill. false = unavailable.
+bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh);
 
 #define GSN_REQUIRE(cond, ...)             \
   do {                                     \

@@ -401,26 +401,7 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   bool tma_ok = false;
-  if (use_tma && W * (long long)C * 2 % 16 == 0) {
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn enc = [] {
-      void *fn = nullptr;
-      cudaDriverEntryPointQueryResult q;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
-      return reinterpret_cast<EncodeFn>(fn);
-    }();
-    if (enc) {
-      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
-      const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-      const cuuint32_t box[4] = {(cuuint32_t)(C / 2), 34, 34, 1};
-      const cuuint32_t estr[4] = {1, 1, 1, 1};
-      tma_ok = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    }
-  }
+  if (use_tma) tma_ok = encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34);
   const __half *xh = reinterpret_cast<const __half *>(x), *wh = reinterpret_cast<const __half *>(wc1);
   __half *oh = reinterpret_cast<__half *>(out);
   if (C == 64) {

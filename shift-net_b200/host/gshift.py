@@ -26,6 +26,7 @@ class GShiftNetB200(nn.Module):
         build_param_tree(self, spec)
         self._engine = None
         self._graphs = {}
+        self.kernel_launches = 0     # kernels of libshiftnet_b200 executed by this module (eager launches + graph replays)
         # Replay the whole forward (~740 kernel launches) as one CUDA graph per input shape: removes the launch gaps
         # between the many short kernels.  Set GSN_CUDA_GRAPH=0 to launch eagerly (profiling per-kernel, debugging).
         import os
@@ -54,26 +55,34 @@ class GShiftNetB200(nn.Module):
         if next(self.parameters()).device != x.device:
             raise RuntimeError("model parameters and input are on different devices; call net.to(device) first")
         eng = self.engine()
+        lib = eng.lib
         if not self.use_cuda_graph or eng.timeline is not None or torch.cuda.is_current_stream_capturing():
-            return eng.forward(x, noise_map, past=self.num_fb, future=self.num_ff)
+            l0 = lib.gsn_launch_count()
+            out = eng.forward(x, noise_map, past=self.num_fb, future=self.num_ff)
+            self.kernel_launches += lib.gsn_launch_count() - l0
+            return out
         key = (tuple(x.shape), x.dtype, None if noise_map is None else tuple(noise_map.shape), self.num_fb, self.num_ff)
         ent = self._graphs.get(key)
         if ent is None:
             # eager warm-up (packs weights, sets kernel attributes, primes the allocator), then capture
             xs = x.clone()
             ns = None if noise_map is None else noise_map.expand(noise_map.shape).clone()
+            l0 = lib.gsn_launch_count()
             eng.forward(xs, ns, past=self.num_fb, future=self.num_ff)
+            self.kernel_launches += lib.gsn_launch_count() - l0
             torch.cuda.synchronize(x.device)
             g = torch.cuda.CUDAGraph()
+            l0 = lib.gsn_launch_count()
             with torch.cuda.graph(g):
                 out_s = eng.forward(xs, ns, past=self.num_fb, future=self.num_ff)
-            ent = (g, xs, ns, out_s)
+            ent = (g, xs, ns, out_s, lib.gsn_launch_count() - l0)   # kernel nodes recorded in the graph
             self._graphs = {key: ent}            # keep one shape at a time (activations of a 720p clip are several GB)
-        g, xs, ns, out_s = ent
+        g, xs, ns, out_s, n_kernels = ent
         xs.copy_(x)
         if ns is not None:
             ns.copy_(noise_map)
         g.replay()
+        self.kernel_launches += n_kernels
         return out_s.clone()
 
 
