@@ -173,7 +173,11 @@ struct TcCfg {
   static constexpr int END1 = S_R + (R12_BYTES > IN_BYTES ? R12_BYTES : IN_BYTES);
   static constexpr bool LATE_WT2 = BOX || TMAIN;   // phase-2 weights go where the box / staging lived: load them later
   static constexpr int SMEM = END1 > END2 ? END1 : END2;
-  static constexpr int S_A2 = S_G1;                                  // GEMM2 operand, then the z staging tile
+  // GEMM2 operand, then the z staging tile.  With TMAIN the kernel is persistent and prefetches the NEXT tile's W1 (at
+  // S_W1) and LN inputs (at S_R) while the current tile is in its tail, so A2/z must not sit on W1: it goes 40 KB into
+  // the (dead) G1 area, still below S_R.
+  static constexpr int S_A2 = TMAIN ? S_G1 + 40 * 1024 : S_G1;
+  static_assert(!TMAIN || (S_A2 >= S_W1 + W1_BYTES && S_A2 + KC2 * P3 <= S_R), "A2 must not overlap the prefetch targets");
   static_assert(2 * CIN * 4 <= 1024 && 9 * HC * 2 <= 704, "X region layout");
   static_assert(KC2 * P3 <= G1_BYTES, "A2 aliases G1");
   static_assert(!LATE_WT2 || S_WT2 >= S_R, "WT2 must sit inside the (dead) gather box / staging, not over A1/W1");
@@ -190,55 +194,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   using K = TcCfg<C, SHIFT, BOX, TMAIN>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = blockIdx.z, x0 = blockIdx.x * K::TW, y0 = blockIdx.y * K::TH;
+  // tiles: linear index = (frame * tiles_y + tile_y) * tiles_x + tile_x.  TMAIN variants are persistent (gridDim.x = #SMs,
+  // stride gridDim.x, next tile's inputs prefetched during the current tile's tail); the others run one tile per CTA.
+  const int tiles_x = (d.W + K::TW - 1) / K::TW, tiles_y = (d.H + K::TH - 1) / K::TH;
+  const int total_tiles = tiles_x * tiles_y * d.T;
+  int tile = blockIdx.x;
+  int t, x0, y0;
+  RollSrc rs;
+  auto decode = [&](int ti) {
+    t = ti / (tiles_x * tiles_y);
+    const int r = ti - t * tiles_x * tiles_y, ty = r / tiles_x;
+    y0 = ty * K::TH;
+    x0 = (r - ty * tiles_x) * K::TW;
+    rs = roll_source(d.mode, d.circular, t, d.T, C);
+  };
+  decode(tile);
   const __half *xg = reinterpret_cast<const __half *>(d.x);
   const unsigned char *wb = reinterpret_cast<const unsigned char *>(d.wblob);
-  const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
   const size_t frame = (size_t)d.H * d.W * C;
   const uint32_t bar = smem_u32(smem + K::S_X + K::X_BAR);
   // debug_stage == 9: thread 0 of every CTA records clock64() at the stage boundaries (profiling aid, tests only)
   long long *clk = (d.debug_stage == 9 && tid == 0)
-                       ? reinterpret_cast<long long *>(d.debug_out) + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16
+                       ? reinterpret_cast<long long *>(d.debug_out) + (size_t)tile * 16
                        : nullptr;
   int clk_i = 0;
-#define GSN_CLK() do { if (clk) clk[clk_i++] = clock64(); } while (0)
+#define GSN_CLK() do { if (clk && clk_i < 16) clk[clk_i++] = clock64(); } while (0)
   GSN_CLK();
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + K::S_X + K::X_TMEM);
 
-  // ---- P0: async loads (small params, W1, gather box / TMA staging), TMEM allocation, barrier init ---------------
+  // ---- P0 (once per CTA): barriers, TMEM, LN params; first tile's loads -------------------------------------------
   const uint32_t bar_in = bar + 8;
-  {
-    if (tid == 32) {
-      mbar_init(bar, 1);
-      mbar_init(bar_in, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
+  if (tid == 32) {
+    mbar_init(bar, 1);
+    mbar_init(bar_in, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  // Loads of one tile that may run ahead of its compute: the LN inputs of the 22x22 region as one (CAB1) or three (CAB2:
+  // rolled low half, rolled high half, shifted half) TMA tile loads -- pixels outside the image arrive as zeros -- and W1.
+  auto issue_inputs = [&](int it, int ix0, int iy0, const RollSrc &irs) {
     if (TMAIN && tid == 0) {
-      // LN inputs of the whole 22x22 region: one (CAB1) or three (CAB2: rolled low half, rolled high half, shifted half)
-      // TMA tile loads; pixels outside the image arrive as zeros.
+      fence_async_proxy();   // earlier generic-proxy accesses of the staging area stay ordered before the TMA writes
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_in), "r"(K::IN_BYTES) : "memory");
       const uint32_t dst = smem_u32(smem + K::S_R);
       auto tma4 = [&](uint32_t sdst, const CUtensorMap *tm, int c0, int f) {
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
-                "r"(sdst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(x0 - 3), "r"(y0 - 3), "r"(f), "r"(bar_in)
+                "r"(sdst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(ix0 - 3), "r"(iy0 - 3), "r"(f), "r"(bar_in)
             : "memory");
       };
       if (SHIFT) {
-        tma4(dst, &tm_x, rs.c_lo, rs.f_lo);
-        tma4(dst + K::M1 * K::HC * 2, &tm_x, rs.c_hi, rs.f_hi);
-        tma4(dst + 2 * K::M1 * K::HC * 2, &tm_hw, 0, t);
+        tma4(dst, &tm_x, irs.c_lo, irs.f_lo);
+        tma4(dst + K::M1 * K::HC * 2, &tm_x, irs.c_hi, irs.f_hi);
+        tma4(dst + 2 * K::M1 * K::HC * 2, &tm_hw, 0, it);
       } else {
-        tma4(dst, &tm_x, 0, t);
+        tma4(dst, &tm_x, 0, it);
       }
     }
+    for (int i = tid; i < K::W1_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
+  };
+  {
+    issue_inputs(t, x0, y0, rs);
     for (int i = tid; i < (K::OFF_W1 - K::OFF_LN) / 16; i += kTcThreads) {  // LN params (+ conv1 weights)
       const int off = i * 16;
       unsigned char *dst = (off < K::OFF_C1) ? smem + K::S_X + K::X_LN + off : smem + K::S_X + K::X_C1 + (off - K::OFF_C1);
       cp_async16(dst, wb + off, true);
     }
-    for (int i = tid; i < K::W1_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
     if (BOX) {
       const bool fwd = d.mode == GSN_MODE_CAB2_FWD;
       const __half *src = xg + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
@@ -267,6 +288,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   const uint32_t tmem = *tmem_slot;
   GSN_CLK();  // 1: loads landed
+  uint32_t in_parity = 0, mma_parity = 0;   // mbarrier phases advance once per completed TMA batch / tcgen05.commit
+  // Prefetch of the next tile's inputs (persistent TMAIN variants), issued once W1 / the staging area of the current tile
+  // are dead.
+  auto prefetch_next = [&]() {
+    if (TMAIN) {
+      const int nt = tile + (int)gridDim.x;
+      if (nt < total_tiles) {
+        const int ntt = nt / (tiles_x * tiles_y), r = nt - ntt * tiles_x * tiles_y, ty = r / tiles_x;
+        const RollSrc nrs = roll_source(d.mode, d.circular, ntt, d.T, C);
+        issue_inputs(ntt, (r - ty * tiles_x) * K::TW, ty * K::TH, nrs);
+        cp_async_commit();
+      }
+    }
+  };
+  for (;;) {   // ---- tile loop (a single iteration for the non-persistent variants) ----
 
   // ---- P1a (BOX): per-channel spatial-shift gather fused with conv1 (dw3x3, zero pad) -> raw A1 planes --------
   if (BOX) {
@@ -366,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     for (int k = 0; k < NV / 8; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { gam[k * 8 + i] = ln_g[chunk_of[k] * 8 + i]; bet[k * 8 + i] = ln_b[chunk_of[k] * 8 + i]; }
-    if (TMAIN) mbar_wait(bar_in, 0);                 // the staged LN inputs have landed
+    if (TMAIN) { mbar_wait(bar_in, in_parity); in_parity ^= 1; }   // the staged LN inputs of this tile have landed
     const unsigned char *stg = smem + K::S_R;
     constexpr int PB = (SHIFT && !BOX) ? 2 : NIT;    // items whose loads are in flight together (register budget)
 #pragma unroll
@@ -460,7 +496,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   if (d.debug_stage == 1) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC1 * K::M1;
+               (size_t)tile * K::KC1 * K::M1;
     for (int i = tid; i < K::KC1 * K::M1; i += kTcThreads)
       o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A1 + (i / K::M1) * K::P1 + (i % K::M1) * 16);
   }
@@ -482,7 +518,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     umma_commit(bar);
   }
   if (K::LATE_WT2) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather / the LayerNorm)
-  mbar_wait(bar, 0);
+  mbar_wait(bar, mma_parity);
+  mma_parity ^= 1;
   tc_fence_after();
   __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
   GSN_CLK();  // GEMM1 done
@@ -568,7 +605,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   if (d.debug_stage == 2) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M2;
+               (size_t)tile * K::KC2 * K::M2;
     for (int i = tid; i < K::KC2 * K::M2; i += kTcThreads)
       o[i] = *reinterpret_cast<uint4 *>(smem + K::S_GT + (i / K::M2) * K::P2 + (i % K::M2) * 16);
   }
@@ -632,7 +669,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   if (d.debug_stage == 3) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M3;
+               (size_t)tile * K::KC2 * K::M3;
     for (int i = tid; i < K::KC2 * K::M3; i += kTcThreads)
       o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A2 + (i / K::M3) * K::P3 + (i % K::M3) * 16);
   }
@@ -673,13 +710,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       }
     }
     __syncthreads();
+    prefetch_next();       // GATED / A2 reads are done: the staging area and W1 are free for the next tile
     if (tid < C) {
-      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = red[tid] + red[C + tid];
+      d.chan_partial[(size_t)tile * C + tid] = red[tid] + red[C + tid];
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512));
-    return;
-  }
+  } else {
 
   // ---- P6: GEMM2 on the tensor core: (256 x C) . W2^T -> TMEM columns [0, 2*N) -------------------------------------
   if (tid == 0) {
@@ -696,10 +731,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       }
     umma_commit(bar);
   }
-  mbar_wait(bar, 1);
+  mbar_wait(bar, mma_parity);
+  mma_parity ^= 1;
   tc_fence_after();
   __syncthreads();                 // A2 is dead: its space becomes the z staging tile
   GSN_CLK();  // GEMM2 done
+  prefetch_next();                 // W1, W2 and the staging area are dead: start the next tile's loads under this tile's tail
 
   // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store + per-tile channel sums ---
   {
@@ -757,11 +794,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     __syncthreads();
     if (tid < C) {
-      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = red[tid] + red[C + tid];
+      d.chan_partial[(size_t)tile * C + tid] = red[tid] + red[C + tid];
     }
   }
   GSN_CLK();  // stores + sums done
+  }   // !MIDCA
+    clk = nullptr;                 // stage clocks are recorded for the first tile of a CTA only
+    if (!TMAIN) break;
+    tile += (int)gridDim.x;
+    if (tile >= total_tiles) break;
+    decode(tile);
+    cp_async_wait<0>();            // the prefetched W1 of this tile has landed
+    tc_fence_before();
+    __syncthreads();               // everyone is done with the previous tile (z staging, TMEM reads, channel sums)
+    tc_fence_after();
+  }   // tile loop
+  __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512));
   }
@@ -776,7 +824,16 @@ static int launch_pass_a_tc(const GsnCabPassA &d, cudaStream_t st, const CUtenso
     attr_set = true;
   }
   static const ShiftTable tab = make_shift_table(C);
-  dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + K::TH - 1) / K::TH, d.T);
+  const long long total = (long long)((d.W + K::TW - 1) / K::TW) * ((d.H + K::TH - 1) / K::TH) * d.T;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  // TMAIN variants are persistent: one CTA per SM walks the tile list and prefetches the next tile's inputs
+  const unsigned grid = (unsigned)(TMAIN ? (total < num_sms ? total : num_sms) : total);
   cab_pass_a_tc_kernel<C, SHIFT, MIDCA, BOX, TMAIN><<<grid, kTcThreads, K::SMEM, st>>>(d, tab, tm_x, tm_hw);
   count_launch();
   return check_launch("cab_pass_a_tc");

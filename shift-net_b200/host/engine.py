@@ -7,6 +7,7 @@ channels padded to a multiple of 16.  No CPU path: constructing an Engine requir
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -32,6 +33,7 @@ class Engine:
         self.shift_split = os.environ.get("GSN_SHIFT_SPLIT", "1") == "1"
         # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
         self.timeline = None
+        self.timeline_detail = os.environ.get("GSN_TIMELINE_DETAIL", "0") == "1"
 
     def _timed(self, name, pixels):
         """Context manager recording CUDA events around one launch on the launching stream (off unless profiling)."""
@@ -114,7 +116,7 @@ class Engine:
         d.chan_partial = partial.data_ptr() if partial is not None else None
         d.dst = dst.data_ptr()
         d.dst_c = dst_c
-        with self._timed("conv_mma", T * Hout * Wout):
+        with self._timed(f"conv_mma[{d.cin_p}>{cout_p} k{ks}s{stride} {Hout}x{Wout}]" if self.timeline_detail else "conv_mma", T * Hout * Wout):
             L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
         return (dst, partial) if want_sums else dst
 
