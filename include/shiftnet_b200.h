@@ -141,7 +141,8 @@ int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, const float
 /* pass A2 (denoise): z = a * sigmoid(b), [a|b] = w2eff_t . u  (1x1 C->2C + SimpleGate2, gshift_denoise2.py:196-197),
  * plus per-tile channel sums of z: chan_partial [T][gsn_cab_tiles_linear(H*W)][C]. */
 int gsn_cab_tiles_linear(long long hw);
-int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C, void *stream);
+int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C,
+                    int per_frame_weights /* 1: w2eff is [T][..] from gsn_cab_fold_mid; 0: one [C/8][2C][8] weight */, void *stream);
 
 /* fold: weff[t] = diag(beta) W3 diag(s_t) as fp16 [T][C/8][C][8] (k-chunk planar), s_t from CALayer2
  * (d2:72-89,238-239,257).  w_du0 [cr][C], w_du2 [C][cr], w3 [C][C], beta [C], bias3 [C] or NULL (fp32).

@@ -522,17 +522,17 @@ __global__ void __launch_bounds__(256) cab_fold_mid_kernel(const float *__restri
 template <int C>
 __global__ void __launch_bounds__(256) cab_pass_a2_kernel(const __half *__restrict__ u, const __half *__restrict__ w2eff,
                                                           __half *__restrict__ z, float *__restrict__ chan_partial,
-                                                          long long hw) {
+                                                          long long hw, size_t w_frame_stride /* halves; 0 = one weight for all frames */) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, N = 2 * C, NTH = C / 8;
-  __shared__ __align__(128) unsigned char su[KC * PZ];
-  __shared__ __align__(128) unsigned char sw[KC * N * 16];
-  __shared__ float red[8 * C];
+  extern __shared__ __align__(128) unsigned char smem_a2[];
+  unsigned char *su = smem_a2, *sw = smem_a2 + KC * PZ;
+  float *red = reinterpret_cast<float *>(smem_a2 + KC * PZ + KC * N * 16);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * MP;
   const size_t frame = (size_t)hw * C;
   {
-    const unsigned char *wg = reinterpret_cast<const unsigned char *>(w2eff) + (size_t)t * N * C * 2;
+    const unsigned char *wg = reinterpret_cast<const unsigned char *>(w2eff + (size_t)t * w_frame_stride);
     for (int i = tid; i < KC * N; i += 256) cp_async16(sw + i * 16, wg + i * 16, true);
     const __half *ug = u + (size_t)t * frame;
     for (int i = tid; i < MP * KC; i += 256) {
@@ -667,17 +667,28 @@ extern "C" int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, 
 extern "C" int gsn_cab_tiles_linear(long long hw) { return (int)((hw + 127) / 128); }
 
 extern "C" int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C,
-                               void *stream) {
+                               int per_frame_weights, void *stream) {
   using namespace gsn;
   GSN_REQUIRE(u && w2eff && z && chan_partial, "cab_pass_a2: null pointer");
   GSN_REQUIRE(T > 0 && H > 0 && W > 0, "cab_pass_a2: empty shape");
   const long long hw = (long long)H * W;
   dim3 grid((unsigned)((hw + 127) / 128), T);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t stride = per_frame_weights ? (size_t)2 * C * C : 0;
   if (C == 64) {
-    cab_pass_a2_kernel<64><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff), reinterpret_cast<__half *>(z), chan_partial, hw);
+    constexpr int smem = 8 * 129 * 16 + 8 * 128 * 16 + 8 * 64 * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(cab_pass_a2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cab_pass_a2_kernel<64><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff),
+                                                    reinterpret_cast<__half *>(z), chan_partial, hw, stride);
+  } else if (C == 80) {
+    constexpr int smem = 10 * 129 * 16 + 10 * 160 * 16 + 8 * 80 * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(cab_pass_a2_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cab_pass_a2_kernel<80><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff),
+                                                    reinterpret_cast<__half *>(z), chan_partial, hw, stride);
   } else {
-    set_error("cab_pass_a2: C=%d unsupported (64)", C);
+    set_error("cab_pass_a2: C=%d unsupported (64, 80)", C);
     return GSN_E_UNSUPPORTED;
   }
   count_launch();

@@ -212,10 +212,9 @@ class Engine:
             wd = sd[p + ".body.1.conv_2.weight"].view(2 * Cc, 9).t().contiguous().half()
             rp = p + f".body.{3 + k}"
             wfrag = P.pack_group_conv5(sd[rp + ".conv_1.weight"], sd[rp + ".conv_2.weight"])
-            w2 = sd[p + f".body.{4 + k}.weight"]
-            sd[p + f".body.{4 + k}#a.weight"], sd[p + f".body.{4 + k}#b.weight"] = w2[:Cc].contiguous(), w2[Cc:].contiguous()
-            self.cache[ck] = (ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k))
-        ln, wc1, wd, wfrag, fw = self.cache[ck]
+            w2p = P.planar_chunks(sd[p + f".body.{4 + k}.weight"].flatten(1)).contiguous()      # [C/8][2C][8] fp16
+            self.cache[ck] = (ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p)
+        ln, wc1, wd, wfrag, fw, w2p = self.cache[ck]
         cin = Cc + Cc // 2 if shift else Cc
         cinp = P.pad16(cin)
         a1 = self._new(T, H, W, cinp)
@@ -245,11 +244,12 @@ class Engine:
         with self._timed("group_conv5", T * H * W):
             L.check(self.lib.gsn_group_conv5(g.data_ptr(), T, H, W, Cc, wfrag.data_ptr(),
                                              s1.data_ptr() if s1 is not None else None, u.data_ptr(), self._stream()), "group_conv5")
-        va = self.conv(p + f".body.{4 + k}#a", [u], [Cc], Cc)
-        vb = self.conv(p + f".body.{4 + k}#b", [u], [Cc], Cc)
+        # second 1x1 (C -> 2C) + SimpleGate2 + per-tile sums in one kernel (u is read once, a|b never touch HBM)
         z = self._new(T, H, W, Cc)
         partial = self._new(T, ntl, Cc, dtype=torch.float32)
-        L.check(self.lib.gsn_gate2(va.data_ptr(), vb.data_ptr(), T, H, W, Cc, z.data_ptr(), partial.data_ptr(), self._stream()), "gate2")
+        with self._timed("cab_pass_a2", T * H * W):
+            L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2p.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 0,
+                                             self._stream()), "cab_pass_a2")
         return self._fold_and_pass_b(p, x, z, partial, ntl, fw, mode)
 
     def shift_cab(self, p, x, c, reverse):
@@ -302,7 +302,7 @@ class Engine:
             partial = self._new(T, ntiles, Cc, dtype=torch.float32)
             z = self._new(T, H, W, Cc)
             with self._timed("cab_pass_a2", T * H * W):
-                L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2eff.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc,
+                L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2eff.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 1,
                                                  self._stream()), "cab_pass_a2")
         out = self._fold_and_pass_b(p, x, z, partial, ntiles, fw, mode)
         if debug_stage:

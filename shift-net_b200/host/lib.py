@@ -79,7 +79,7 @@ def load():
     lib.gsn_cab_pass_b.argtypes = [C.POINTER(CabPassB), vp]
     lib.gsn_cab_fold_mid.argtypes = [vp, i, f, vp, vp, i, vp, i, i, vp, vp]
     lib.gsn_cab_tiles_linear.argtypes = [ll]
-    lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
     lib.gsn_shift_conv1.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp]
     lib.gsn_shift_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, i, vp, vp]
     lib.gsn_dw_gate.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
