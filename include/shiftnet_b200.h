@@ -173,6 +173,10 @@ int gsn_cab_pass_b(const GsnCabPassB *d, void *stream);
  * wc1: fp16 [9][C/2] (CAB2 modes); ln: fp32 gamma[cin] then beta[cin]. */
 int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
                  void *out, int cinp, const void *hw_pre /* optional (T,H,W,C/2) from gsn_shift_conv1 */, void *stream);
+/* LayerNorm + first 1x1 fused: [rolled stream | hw_pre] -> LN -> W1 -> (ga | gb), each (T,H,W,C) fp16.
+ * w1p: fp16 [K/8 padded to even][2C][8] (k-chunk planar, zero-padded K); ln: fp32 gamma[cin], beta[cin]. */
+int gsn_ln_pw(const void *x, const void *hw_pre, int T, int H, int W, int C, int mode, int circular, const float *ln,
+              const void *w1p, void *ga, void *gb, void *stream);
 /* g = (dw3x3(a)+a) * (dw3x3(b)+b) (RepConv2 + SimpleGate); wd fp16 [9][2C]; partial (optional) [T][tiles_linear][C]. */
 int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,
                 void *stream);

@@ -10,6 +10,7 @@
 //   cab_fold / cab_pass_b (shift_cab.cu)
 //
 // Same zero-padding rules and the same deterministic per-tile partial sums as the fused path.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -100,6 +101,111 @@ __global__ void __launch_bounds__(256) shift_ln_kernel(const __half *__restrict_
 #pragma unroll
     for (int i = 0; i < 8; ++i) o8[i] = (cb < cin) ? (v[i] - mu) * rstd * __ldg(ln + cb + i) + __ldg(ln + cin + cb + i) : 0.f;
     *reinterpret_cast<uint4 *>(out + ((size_t)t * hw + pix) * cinp + cb) = pack8(o8);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// ln_pw: [rolled stream | shift_conv1 output] -> LayerNorm -> first 1x1 (C' -> 2C) in one kernel; the two halves of the
+// result (a | b) are written as separate (T,H,W,C) tensors for dw_gate.  128 pixels per CTA, k-chunk planar operands,
+// mma.sync m16n8k16 with fp32 accumulation; the LayerNorm input never makes a round trip through HBM.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) ln_pw_kernel(const __half *__restrict__ x, const __half *__restrict__ hw_pre, int T,
+                                                    long long hw, int mode, int circular, const float *__restrict__ ln,
+                                                    const __half *__restrict__ w1p /*[KCP][2C][8]*/,
+                                                    __half *__restrict__ ga, __half *__restrict__ gb) {
+  constexpr int MP = 128, PZ = (MP + 1) * 16, N = 2 * C, HC = C / 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const bool shift = mode != GSN_MODE_CAB1;
+  const int cin = shift ? C + HC : C, kc = cin / 8, kcp = (kc + 1) / 2 * 2;   // chunks, padded to whole k-steps
+  unsigned char *sa = smem, *sw = smem + 16 * PZ;                           // A planes (<= 16), W planes [kcp][N]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * MP;
+  const size_t frame = (size_t)hw * C;
+  const RollSrc rs = roll_source(mode, circular, t, T, C);
+  for (int i = tid; i < kcp * N; i += 256) cp_async16(sw + i * 16, reinterpret_cast<const unsigned char *>(w1p) + (size_t)i * 16, true);
+  for (int i = tid; i < MP * kcp; i += 256) {
+    const int ch = i % kcp, p = i / kcp;
+    const bool valid = (p0 + p < hw) && ch < kc;
+    const size_t pix = valid ? (size_t)(p0 + p) : 0;
+    const __half *sp = x;
+    if (valid) {
+      const int cb = ch * 8;
+      if (!shift) sp = x + (size_t)t * frame + pix * C + cb;
+      else if (cb < HC) sp = x + rs.f_lo * frame + pix * C + rs.c_lo + cb;
+      else if (cb < C) sp = x + rs.f_hi * frame + pix * C + rs.c_hi + cb - HC;
+      else sp = hw_pre + ((size_t)t * hw + pix) * HC + cb - C;
+    }
+    cp_async16(sa + ch * PZ + p * 16, sp, valid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  {  // LayerNorm: two threads per pixel, each owns every other chunk; biased variance, eps 1e-6 (d2:19-28)
+    const int p = tid >> 1, hsel = tid & 1;
+    float s = 0.f;
+    for (int ch = hsel; ch < kc; ch += 2) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4 *>(sa + ch * PZ + p * 16), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const float mu = s / cin;
+    float ss = 0.f;
+    for (int ch = hsel; ch < kc; ch += 2) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4 *>(sa + ch * PZ + p * 16), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    const float rstd = rsqrtf(ss / cin + 1e-6f);
+    for (int ch = hsel; ch < kc; ch += 2) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4 *>(sa + ch * PZ + p * 16), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rstd * __ldg(ln + ch * 8 + i) + __ldg(ln + cin + ch * 8 + i);
+      *reinterpret_cast<uint4 *>(sa + ch * PZ + p * 16) = pack8(v);
+    }
+  }
+  __syncthreads();
+  constexpr int NTP = N / 16;   // n-tile pairs
+  float acc[2 * NTP][4];
+#pragma unroll
+  for (int n = 0; n < 2 * NTP; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+  const uint32_t a_s = smem_u32(sa), w_s = smem_u32(sw);
+  for (int k = 0; k < kcp / 2; ++k) {
+    uint32_t a[4];
+    ldmatrix_x4(a[0], a[1], a[2], a[3], a_s + (2 * k + (lane >> 4)) * PZ + (warp * 16 + (lane & 15)) * 16);
+#pragma unroll
+    for (int np = 0; np < NTP; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4(b[0], b[1], b[2], b[3], w_s + ((2 * k + ((lane >> 3) & 1)) * N + np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * 16);
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+  __syncthreads();             // every warp is done with the weight planes: reuse them as the output staging tile
+  const int g = lane >> 2, tig = lane & 3;
+  unsigned char *so = sw;      // [2C/8 planes][MP+1] x 16 B  (= N/8 * PZ <= kcp * N * 16 for C in {64, 80})
+#pragma unroll
+  for (int n = 0; n < 2 * NTP; ++n)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow)
+      *reinterpret_cast<uint32_t *>(so + n * PZ + (warp * 16 + g + hrow * 8) * 16 + tig * 4) = pack_half2(acc[n][hrow * 2], acc[n][hrow * 2 + 1]);
+  __syncthreads();
+  constexpr int CHN = C / 8;
+  for (int i = tid; i < MP * 2 * CHN; i += 256) {
+    const int ch = i % (2 * CHN), p = i / (2 * CHN);
+    if (p0 + p < hw) {
+      __half *dst = (ch < CHN ? ga : gb) + ((size_t)t * hw + p0 + p) * C + (ch % CHN) * 8;
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(so + ch * PZ + p * 16);
+    }
   }
 }
 
@@ -428,6 +534,26 @@ extern "C" int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode,
       reinterpret_cast<__half *>(out), cinp, reinterpret_cast<const __half *>(hw_pre));
   count_launch();
   return check_launch("shift_ln");
+}
+
+extern "C" int gsn_ln_pw(const void *x, const void *hw_pre, int T, int H, int W, int C, int mode, int circular, const float *ln,
+                         const void *w1p, void *ga, void *gb, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(x && ln && w1p && ga && gb, "ln_pw: null pointer");
+  GSN_REQUIRE(mode == GSN_MODE_CAB1 || hw_pre, "ln_pw: CAB2 modes need the shift_conv1 output");
+  GSN_REQUIRE(T > 0 && H > 0 && W > 0, "ln_pw: empty shape");
+  if (C != 80) { set_error("ln_pw: C=%d unsupported (80)", C); return GSN_E_UNSUPPORTED; }
+  const long long hw = (long long)H * W;
+  const int kc = (mode == GSN_MODE_CAB1 ? C : C + C / 2) / 8, kcp = (kc + 1) / 2 * 2;
+  const int smem = 16 * 129 * 16 + std::max(kcp * 2 * C * 16, 2 * C / 8 * 129 * 16);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(ln_pw_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16 + 20 * 129 * 16); attr = true; }
+  dim3 grid((unsigned)((hw + 127) / 128), T);
+  ln_pw_kernel<80><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(x), reinterpret_cast<const __half *>(hw_pre), T, hw, mode, circular, ln,
+      reinterpret_cast<const __half *>(w1p), reinterpret_cast<__half *>(ga), reinterpret_cast<__half *>(gb));
+  count_launch();
+  return check_launch("ln_pw");
 }
 
 extern "C" int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,

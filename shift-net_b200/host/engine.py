@@ -207,29 +207,29 @@ class Engine:
         if ck not in self.cache:
             ln = torch.cat((sd[p + ".norm.weight"], sd[p + ".norm.bias"])).contiguous()
             wc1 = sd[p + ".conv1.weight"].view(Cc // 2, 9).t().contiguous().half() if shift else None
-            w1 = sd[p + ".body.0.weight"]
-            sd[p + ".body.0#a.weight"], sd[p + ".body.0#b.weight"] = w1[:Cc].contiguous(), w1[Cc:].contiguous()
+            w1 = sd[p + ".body.0.weight"].flatten(1)                              # (2C, cin)
+            kpad = (w1.shape[1] + 15) // 16 * 16
+            w1z = torch.zeros(w1.shape[0], kpad, device=w1.device)
+            w1z[:, :w1.shape[1]] = w1
+            w1p = P.planar_chunks(w1z).contiguous()                              # [kpad/8][2C][8], zero-padded K
             wd = sd[p + ".body.1.conv_2.weight"].view(2 * Cc, 9).t().contiguous().half()
             rp = p + f".body.{3 + k}"
             wfrag = P.pack_group_conv5(sd[rp + ".conv_1.weight"], sd[rp + ".conv_2.weight"])
             w2p = P.planar_chunks(sd[p + f".body.{4 + k}.weight"].flatten(1)).contiguous()      # [C/8][2C][8] fp16
-            self.cache[ck] = (ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p)
-        ln, wc1, wd, wfrag, fw, w2p = self.cache[ck]
-        cin = Cc + Cc // 2 if shift else Cc
-        cinp = P.pad16(cin)
-        a1 = self._new(T, H, W, cinp)
+            self.cache[ck] = (ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p, w1p)
+        ln, wc1, wd, wfrag, fw, w2p, w1p = self.cache[ck]
         hw_pre = None
         if shift:      # gather folded into conv1's load stage (TMA-staged box), written once, read by the LayerNorm kernel
             hw_pre = self._new(T, H, W, Cc // 2)
             with self._timed("shift_conv1", T * H * W):
                 L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0, wc1.data_ptr(),
                                                  hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
-        with self._timed("shift_ln", T * H * W):
-            L.check(self.lib.gsn_shift_ln(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0,
-                                          wc1.data_ptr() if wc1 is not None else None, ln.data_ptr(), a1.data_ptr(), cinp,
-                                          hw_pre.data_ptr() if hw_pre is not None else None, self._stream()), "shift_ln " + p)
-        ga = self.conv(p + ".body.0#a", [a1], [cin], Cc)
-        gb = self.conv(p + ".body.0#b", [a1], [cin], Cc)
+        # LayerNorm + first 1x1 in one kernel (the 1.5C-wide LN input never goes to HBM), a|b halves written separately
+        ga, gb = self._new(T, H, W, Cc), self._new(T, H, W, Cc)
+        with self._timed("ln_pw", T * H * W):
+            L.check(self.lib.gsn_ln_pw(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
+                                       1 if self.spec.circular else 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                       self._stream()), "ln_pw " + p)
         ntl = self.lib.gsn_cab_tiles_linear(H * W)
         g = self._new(T, H, W, Cc)
         pg = self._new(T, ntl, Cc, dtype=torch.float32) if self.spec.denoise else None
