@@ -69,6 +69,29 @@ typedef struct {
 int gsn_conv_tiles(int Hout, int Wout);
 int gsn_conv_mma(const GsnConvDesc *d, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused body of the dense channel-attention block: r = conv3x3(PReLU(conv3x3(x))) in ONE kernel (the intermediate
+ * stays in shared memory) plus the per-tile channel sums of r for the CALayer pooling.  Replaces the two nn.Conv2d
+ * and the nn.PReLU of CAB.body (d2:143-150,154); gsn_ca_scale + gsn_scale_residual finish the block (d2:155-158).
+ * x, r: (T,H,W,cp) NHWC fp16, cp = 16 or 24 (wider CABs keep using two gsn_conv_mma launches); r must not alias x.
+ * w1pack / w2pack: fp16 weights in mma B-fragment order [tap = ky*3+kx][cp/8][2*(cp/16) + (cp%16)/8 words][32 lanes]
+ * (host/packing.py pack_dense_frag); bias1 / bias2: cp floats or NULL.
+ * chan_partial: [T][gsn_cab_dense_tiles(cp,H,W)][cp] fp32 or NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int T, H, W, cp;
+  const void *x;
+  const void *w1pack, *w2pack;
+  const float *bias1, *bias2;
+  int has_prelu;
+  float prelu_slope;
+  void *r;
+  float *chan_partial;
+} GsnCabDense;
+
+int gsn_cab_dense_tiles(int cp, int H, int W);
+int gsn_cab_dense(const GsnCabDense *d, void *stream);
+
 /* First conv: NCHW user clip -> NHWC features. Replaces feat_extract[0] (d2:710), including the
  * x[0] un-batching of d2:750 and (denoise) the torch.cat((x, noise_map)) of gshift_denoise2.py:749.
  * x: (T,cin,H,W) fp16 or fp32; w: fp32 [9][cin][cout_p]; bias: fp32 [cout_p]; dst NHWC fp16. */

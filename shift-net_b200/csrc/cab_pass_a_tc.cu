@@ -157,7 +157,7 @@ struct TcCfg {
   static constexpr int P1 = (M1 + 1) * 16, P2 = (M2 + 1) * 16, P3 = (M3 + 1) * 16;
   // shared memory map.  Phase 1: [X | W1 | A1 | R12]; phase 2: [X | G1 ........ | GATED | WT2], A2/Z alias G1.
   static constexpr int S_X = 0;                                      // LN params, conv1 weights, barrier, tmem ptr, sums
-  static constexpr int X_LN = 0, X_C1 = 1024, X_BAR = 1728, X_TMEM = 1744, X_RED = 1792, X_BYTES = 1792 + 2 * C * 4;
+  static constexpr int X_LN = 0, X_C1 = 1024, X_BAR = 1728, X_TMEM = 1744, X_RED = 1792, X_BYTES = 1792 + 16 * 32 * 4;   // X_RED: [16 warps][32] channel-sum partials
   static constexpr int S_W1 = (X_BYTES + 127) / 128 * 128;
   static constexpr int S_A1 = S_W1 + W1_BYTES;
   static constexpr int A1_BYTES = KC1 * P1;
@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     constexpr int NV = SHIFT ? 24 : 16;
     constexpr int ITEMS = (K::M1 + 7) / 8 * 8 * 4;   // whole warps only (quad shuffles below)
     constexpr int NIT = (ITEMS + kTcThreads - 1) / kTcThreads;
+    static_assert(NIT == K::MT1 && kTcThreads == 4 * 128, "one LayerNorm iteration = one UMMA M tile");
     const int j = tid & 3;                            // the quad lane never changes across a thread's items
     int chunk_of[NV / 8];
     if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
@@ -459,35 +460,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
             for (int i = 16; i < NV; ++i) v[i] = 0.f;
           }
         }
-        float s = 0.f;
+        // one pass: s1 = sum v, s2 = sum v^2 (fp32; |mu| <~ sigma here, so E[v^2] - mu^2 loses nothing that matters in fp16)
+        float s = 0.f, ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) s += v[i];
+        for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float mu = s * (1.f / K::CIN);
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
         ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
         ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        const float rstd = inimg ? rsqrtf(ss * (1.f / K::CIN) + 1e-6f) : 0.f;   // rstd = 0 and beta masked => zero row
+        const float mu = s * (1.f / K::CIN);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / K::CIN) - mu * mu, 0.f) + 1e-6f);
+        const float nmr = -mu * rstd;
         if (q < K::M1) {
+          if (inimg) {
 #pragma unroll
-          for (int k = 0; k < NV / 8; ++k) {
-            float o[8];
+            for (int k = 0; k < NV / 8; ++k) {
+              float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float a = rstd * gam[k * 8 + i];
-              o[i] = fmaf(v[k * 8 + i], a, (inimg ? bet[k * 8 + i] : 0.f) - mu * a);
+              for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[k * 8 + i], rstd, nmr), gam[k * 8 + i], bet[k * 8 + i]);
+              *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
             }
-            *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
+          } else {                                       // outside the image: the 1x1 sees zero padding (P3 of SURVEY.md)
+#pragma unroll
+            for (int k = 0; k < NV / 8; ++k)
+              *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = make_uint4(0, 0, 0, 0);
           }
         }
       }
+      // M tile `it` of A1 (pixels [128 it, 128 it + 128)) is complete: hand it to the tensor core while the LayerNorm of the
+      // next M tile runs.  GEMM1: D[m] (128 x 2C, TMEM) = A1[m] (128 x CIN) . W1^T
+      fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_f16(128, K::N);
+        const uint32_t a_s = smem_u32(smem + K::S_A1), w_s = smem_u32(smem + K::S_W1);
+#pragma unroll
+        for (int k = 0; k < K::KC1 / 2; ++k) {
+          const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P1 + it * 128 * 16, K::P1, 128);
+          const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
+          umma_f16(tmem + it * K::N, ad, bd, idesc, k > 0);
+        }
+        if (it == NIT - 1) umma_commit(bar);
+      }
     }
     }
-    fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
-    __syncthreads();
     GSN_CLK();  // LN done
     if (TMAIN) {           // the staging area is dead: stream the phase-2 weights (dw taps + W2) into its place
       for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
@@ -501,22 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A1 + (i / K::M1) * K::P1 + (i % K::M1) * 16);
   }
 
-  // ---- P2: GEMM1 on the tensor core: D[m-tile] (128 x 2C, TMEM) = A1 (128 x CIN) . W1^T ----------------------
-  if (tid == 0) {
-    tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_f16(128, K::N);
-    const uint32_t a_s = smem_u32(smem + K::S_A1), w_s = smem_u32(smem + K::S_W1);
-#pragma unroll 1
-    for (int m = 0; m < K::MT1; ++m) {
-#pragma unroll
-      for (int k = 0; k < K::KC1 / 2; ++k) {
-        const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P1 + m * 128 * 16, K::P1, 128);
-        const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
-        umma_f16(tmem + m * K::N, ad, bd, idesc, k > 0);
-      }
-    }
-    umma_commit(bar);
-  }
+  // ---- P2: GEMM1 was issued M tile by M tile from inside the LayerNorm loop; wait for the last one -----------------
   if (K::LATE_WT2) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather / the LayerNorm)
   mbar_wait(bar, mma_parity);
   mma_parity ^= 1;
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
 
   // ---- P4: dw3x3 + id on both halves, SimpleGate -> GATED (zero outside the image) ---------------------------------
+  // The identity of RepConv2 / RepConv is folded into the centre tap by host/packing.py (w_c + 1 in fp16).
   {
     constexpr int NSTRIP = 3, SROWS = (K::R2H + NSTRIP - 1) / NSTRIP;  // 7,7,6 output rows
     const unsigned char *wda = smem + K::S_WT2;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
         H8 w[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) w[i] = lds_h8(wda + (i * 2 * C + chunk * 8) * 2);
-        H8 acc0, acc1, ctr_prev;
+        H8 acc0, acc1;
 #pragma unroll
         for (int i = 0; i < SROWS + 2; ++i) {           // input region row r0 + i feeds output rows (r0+i-2 .. r0+i)
           const int row = r0 + i;
@@ -574,8 +577,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
             const H8 v0 = lds_h8(rp), v1 = lds_h8(rp + 16), v2 = lds_h8(rp + 32);
             if (i >= 2) {                               // output row r0+i-2 completes with kernel row 2
               h8_fma(acc0, v0, w[6]); h8_fma(acc0, v1, w[7]); h8_fma(acc0, v2, w[8]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc0.h[q] = __hadd2(acc0.h[q], ctr_prev.h[q]);   // + identity (RepConv2)
               if (half == 0) res[i - 2] = acc0;
               else {
                 const int orow = row - 2;
@@ -591,8 +592,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
             }
             if (i >= 1) {                               // output row r0+i-1: kernel row 1 (centre row)
               acc0 = acc1;
-              h8_fma(acc0, v0, w[3]); h8_fma(acc0, v1, w[4]); h8_fma(acc0, v2, w[5]);
-              ctr_prev = v1;
+              h8_fma(acc0, v0, w[3]); h8_fma(acc0, v1, w[4]); h8_fma(acc0, v2, w[5]);   // w[4] carries the "+ x" of RepConv2
             }
             h8_mul(acc1, v0, w[0]);                     // output row r0+i: kernel row 0 starts a new accumulator
             h8_fma(acc1, v1, w[1]); h8_fma(acc1, v2, w[2]);
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
         w[i][0] = *reinterpret_cast<const __half2 *>(&ww.x);
         w[i][1] = *reinterpret_cast<const __half2 *>(&ww.y);
       }
-      __half2 acc[5][2], ctr[3][2];
+      __half2 acc[5][2];
 #pragma unroll
       for (int i = 0; i < SROWS + 4; ++i) {             // gated row r0 + i feeds output rows r0+i-4 .. r0+i
         const unsigned char *rp = pl + ((r0 + i) * K::R2W + x) * 16;
@@ -650,15 +650,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
             for (int e = 0; e < 2; ++e)
               acc[s][e] = (ky == 0 && tx == 0) ? __hmul2(v[tx][e], w[ky * 5 + tx][e]) : __hfma2(v[tx][e], w[ky * 5 + tx][e], acc[s][e]);
         }
-        // centre value of gated row r0+i is the identity term of output row oi = i - 2
-        ctr[i % 3][0] = v[2][0]; ctr[i % 3][1] = v[2][1];
         const int od = i - 4;                           // output row completed by this input row
         if (od >= 0) {
-          const int s = od % 5, cs = (od + 2) % 3;
+          const int s = od % 5;
           uint2 o;
-          __half2 o0 = __hadd2(acc[s][0], ctr[cs][0]), o1 = __hadd2(acc[s][1], ctr[cs][1]);
-          o.x = *reinterpret_cast<uint32_t *>(&o0);
-          o.y = *reinterpret_cast<uint32_t *>(&o1);
+          o.x = *reinterpret_cast<uint32_t *>(&acc[s][0]);
+          o.y = *reinterpret_cast<uint32_t *>(&acc[s][1]);
           *reinterpret_cast<uint2 *>(smem + K::S_A2 + (hc >> 1) * K::P3 + ((r0 + od) * K::TW + x) * 16 + (hc & 1) * 8) = o;
         }
       }
@@ -738,23 +735,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   GSN_CLK();  // GEMM2 done
   prefetch_next();                 // W1, W2 and the staging area are dead: start the next tile's loads under this tile's tail
 
-  // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store + per-tile channel sums ---
+  // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store; per-tile channel sums --------
   {
     const int quarter = warp & 3, sub = warp >> 2;
-    for (int u = sub; u < K::MT3 * (C / 32); u += kTcThreads / 128) {
-      const int m = u / (C / 32), cg = u % (C / 32);
+    float *red = reinterpret_cast<float *>(smem + K::S_X + K::X_RED);   // [16 warps][32 channels]
+    static_assert(K::MT3 * (C / 32) == kTcThreads / 128, "one (M tile, 32-channel group) unit per warp");
+    {
+      const int m = sub / (C / 32), cg = sub % (C / 32);
       uint32_t a[32], b[32];
       const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32;
       tmem_ld32(base, a);
       tmem_ld32(base + C, b);
       const int px = m * 128 + quarter * 32 + lane;
+      const bool valid = (y0 + px / K::TW < d.H) && (x0 + px % K::TW < d.W);
+      float z[32];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        float z[8];
+      for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(a[i]) * sigmoid_tanh(__uint_as_float(b[i]));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = __uint_as_float(a[c4 * 8 + i]) * sigmoid_tanh(__uint_as_float(b[c4 * 8 + i]));
-        *reinterpret_cast<uint4 *>(smem + K::S_A2 + (cg * 4 + c4) * K::P3 + px * 16) = pack8(z);
+      for (int c4 = 0; c4 < 4; ++c4)
+        *reinterpret_cast<uint4 *>(smem + K::S_A2 + (cg * 4 + c4) * K::P3 + px * 16) = pack8(*reinterpret_cast<float(*)[8]>(&z[c4 * 8]));
+      // sum over the warp's 32 pixels of each of its 32 channels: butterfly that halves the live values per step;
+      // lane l ends up with channel cg*32 + l (fixed order => deterministic)
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0.f;
       }
+#pragma unroll
+      for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = lane & off;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const float send = hi ? z[i] : z[i + n], keep = hi ? z[i + n] : z[i];
+          z[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      red[warp * 32 + lane] = z[0];
     }
     tc_fence_before();
     __syncthreads();
@@ -766,35 +781,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       if (gy < d.H && gx < d.W)
         *reinterpret_cast<uint4 *>(zg + ((size_t)gy * d.W + gx) * C + ch * 8) = *reinterpret_cast<const uint4 *>(smem + K::S_A2 + ch * K::P3 + p * 16);
     }
-    // deterministic channel sums: warp = (chunk, pixel half), lanes stride the pixels, shuffle tree, 2 partials per chunk
-    float *red = reinterpret_cast<float *>(smem + K::S_X + K::X_RED);
-    for (int u = warp; u < K::KC2 * 2; u += kTcThreads / 32) {
-      const int ch = u % K::KC2, hf = u / K::KC2;
-      float s[8];
+    if (tid < C) {   // channel tid = group cg, lane l: the 8 warps (4 lane quarters x 2 M tiles) that own the group
+      const int cg = tid >> 5, l = tid & 31;
+      float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] = 0.f;
-      for (int p = hf * (K::M3 / 2) + lane; p < (hf + 1) * (K::M3 / 2); p += 32) {
-        const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
-        if (gy < d.H && gx < d.W) {
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4 *>(smem + K::S_A2 + ch * K::P3 + p * 16), f);
+      for (int m = 0; m < K::MT3; ++m)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] += f[i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) red[hf * C + ch * 8 + i] = s[i];
-      }
-    }
-    __syncthreads();
-    if (tid < C) {
-      d.chan_partial[(size_t)tile * C + tid] = red[tid] + red[C + tid];
+        for (int qq = 0; qq < 4; ++qq) s += red[(qq + 4 * (m * (C / 32) + cg)) * 32 + l];
+      d.chan_partial[(size_t)tile * C + tid] = s;
     }
   }
   GSN_CLK();  // stores + sums done

@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) cab_pass_a_kernel(const GsnCabPas
           const unsigned char *pa = smem + K::S_G1S + jj * K::P1;
           const unsigned char *pb = smem + K::S_G1S + (2 + jj) * K::P1;
           const int ctr = (ry + 1) * K::R1W + rx + 1;
-          unpack8(*reinterpret_cast<const uint4 *>(pa + ctr * 16), aa);
-          unpack8(*reinterpret_cast<const uint4 *>(pb + ctr * 16), bb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) aa[i] = bb[i] = 0.f;   // the "+ x" of RepConv2 is folded into the centre tap (host/packing.py)
 #pragma unroll
           for (int ty = 0; ty < 3; ++ty)
 #pragma unroll
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) cab_pass_a_kernel(const GsnCabPas
       const int oy = p / K::TW, ox = p - oy * K::TW;
       const unsigned char *pg = smem + K::S_GT + ch * K::P2;
       float acc[8];
-      unpack8(*reinterpret_cast<const uint4 *>(pg + ((oy + 2) * K::R2W + ox + 2) * 16), acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;             // identity folded into the centre tap
 #pragma unroll
       for (int ty = 0; ty < 5; ++ty)
 #pragma unroll

@@ -31,6 +31,8 @@ class Engine:
         # shifted+conv1'd half (C/2 channels) and pass A reads it in its LayerNorm load stage.
         import os
         self.shift_split = os.environ.get("GSN_SHIFT_SPLIT", "1") == "1"
+        # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
+        self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"
         # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
         self.timeline = None
         self.timeline_detail = os.environ.get("GSN_TIMELINE_DETAIL", "0") == "1"
@@ -121,10 +123,35 @@ class Engine:
         return (dst, partial) if want_sums else dst
 
     # ------------------------------------------------------------------ CAB (dense 3x3 + channel attention)
+    def cab_body_fused(self, p, x, c):
+        """conv3x3 -> PReLU -> conv3x3 of CAB.body (gshift_deblur2.py:146-150) in one kernel (csrc/cab_dense.cu)."""
+        T, H, W, cp = x.shape
+        ck = ("cab_dense", p)
+        if ck not in self.cache:
+            b1, b2 = self.sd.get(p + ".body.0.bias"), self.sd.get(p + ".body.2.bias")
+            self.cache[ck] = (P.pack_dense_frag(self.sd[p + ".body.0.weight"], cp), P.pack_dense_frag(self.sd[p + ".body.2.weight"], cp),
+                              P.pack_bias(b1, cp) if b1 is not None else None, P.pack_bias(b2, cp) if b2 is not None else None)
+        w1, w2, b1, b2 = self.cache[ck]
+        r = self._new(T, H, W, cp)
+        partial = self._new(T, self.lib.gsn_cab_dense_tiles(cp, H, W), cp, dtype=torch.float32)
+        d = L.CabDense()
+        d.T, d.H, d.W, d.cp = T, H, W, cp
+        d.x, d.w1pack, d.w2pack = x.data_ptr(), w1.data_ptr(), w2.data_ptr()
+        d.bias1 = b1.data_ptr() if b1 is not None else None
+        d.bias2 = b2.data_ptr() if b2 is not None else None
+        d.has_prelu, d.prelu_slope = 1, self._slope(p + ".body.1.weight")
+        d.r, d.chan_partial = r.data_ptr(), partial.data_ptr()
+        with self._timed(f"cab_dense[{cp} {H}x{W}]" if self.timeline_detail else "cab_dense", T * H * W):
+            L.check(self.lib.gsn_cab_dense(C.byref(d), self._stream()), "cab_dense " + p)
+        return r, partial
+
     def cab(self, p, x, c, extra=None):
         """gshift_deblur2.py:143-158.  ``extra`` is an optional tensor added to the result (stage shortcuts)."""
-        r1 = self.conv(p + ".body.0", [x], [c], c, prelu_key=p + ".body.1.weight")
-        r2, partial = self.conv(p + ".body.2", [r1], [c], c, want_sums=True)
+        if self.cab_fused and x.shape[3] in (16, 24):
+            r2, partial = self.cab_body_fused(p, x, c)
+        else:
+            r1 = self.conv(p + ".body.0", [x], [c], c, prelu_key=p + ".body.1.weight")
+            r2, partial = self.conv(p + ".body.2", [r1], [c], c, want_sums=True)
         ck = ("ca", p)
         if ck not in self.cache:
             self.cache[ck] = (self.sd[p + ".CA.conv_du.0.weight"].flatten(1).contiguous(),

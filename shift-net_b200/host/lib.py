@@ -15,6 +15,7 @@ EXPORTS = [
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
     "gsn_shift_conv1", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
+    "gsn_cab_dense_tiles", "gsn_cab_dense",
 ]
 
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
@@ -29,6 +30,14 @@ class ConvDesc(C.Structure):
         ("wpack", C.c_void_p), ("bias", C.c_void_p), ("has_prelu", C.c_int), ("prelu_slope", C.c_float),
         ("residual", C.c_void_p), ("pixel_shuffle", C.c_int), ("chan_partial", C.c_void_p), ("dst", C.c_void_p),
         ("dst_c", C.c_int),
+    ]
+
+
+class CabDense(C.Structure):
+    _fields_ = [
+        ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("cp", C.c_int), ("x", C.c_void_p), ("w1pack", C.c_void_p),
+        ("w2pack", C.c_void_p), ("bias1", C.c_void_p), ("bias2", C.c_void_p), ("has_prelu", C.c_int),
+        ("prelu_slope", C.c_float), ("r", C.c_void_p), ("chan_partial", C.c_void_p),
     ]
 
 
@@ -87,6 +96,8 @@ def load():
     lib.gsn_gate2.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.gsn_group_conv5.argtypes = [vp, i, i, i, i, vp, vp, vp, vp]
     lib.gsn_roll_copy.argtypes = [vp, vp, i, i, i, i, i, i, vp]
+    lib.gsn_cab_dense_tiles.argtypes = [i, i, i]
+    lib.gsn_cab_dense.argtypes = [C.POINTER(CabDense), vp]
     for n in EXPORTS:
         fn = getattr(lib, n)
         if fn.restype is C.c_int and n not in ("gsn_version", "gsn_conv_tiles", "gsn_cab_tiles"):

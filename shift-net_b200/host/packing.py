@@ -38,6 +38,22 @@ def pack_conv_mma(w: torch.Tensor, src_real, src_pad, cout_p: int) -> torch.Tens
     return v.reshape(-1).half()
 
 
+def pack_dense_frag(w: torch.Tensor, cp: int) -> torch.Tensor:
+    """Dense 3x3 conv weight (cout, cin, 3, 3), cout, cin <= cp -> fp16 mma B fragments for csrc/cab_dense.cu:
+    [tap = ky*3+kx][cp/8 n-tiles][words][32 lanes] of 32-bit words (two fp16: k, k+1), words = 2 per 16-channel k-step
+    (k = 16s + 2*tig + e ; then + 8) followed by one word for an 8-channel tail (cp % 16 == 8); lane = g*4 + tig, n = nt*8 + g."""
+    w = w.float()
+    cout, cin, k, _ = w.shape
+    assert k == 3 and cout <= cp and cin <= cp and cp % 8 == 0
+    wp = torch.zeros(cp, cp, 9, device=w.device)
+    wp[:cout, :cin] = w.reshape(cout, cin, 9)
+    nt, k16, k8 = cp // 8, cp // 16, (cp % 16) // 8
+    v = wp.view(nt, 8, cp // 8, 4, 2, 9)              # (nt, g, kchunk, tig, e, tap): k = kchunk*8 + 2*tig + e
+    v = v.permute(5, 0, 2, 1, 3, 4).contiguous()      # (tap, nt, kchunk, g, tig, e): word index = kchunk, lane = g*4 + tig
+    assert v.shape[2] == 2 * k16 + k8
+    return v.reshape(-1).half()
+
+
 def pack_conv_in(w, b, cout_p):
     """(cout, cin, 3, 3) -> fp32 [9][cin][cout_p], bias [cout_p] (csrc/io_convs.cu conv_in)."""
     cout, cin = w.shape[:2]
@@ -83,12 +99,15 @@ def pack_cab_pass_a(sd, p, C, shift, body_off=0):
         parts.append(c1.view(torch.uint8).reshape(-1))
     w1 = sd[p + ".body.0.weight"].float().flatten(1)                                       # (2C, CIN)
     parts.append(planar_chunks(w1).view(torch.uint8).reshape(-1))
-    da = sd[p + ".body.1.conv_2.weight"].float().view(2 * C, 9).t().contiguous().half()   # [9][2C]
+    da = sd[p + ".body.1.conv_2.weight"].float().view(2 * C, 9).t().contiguous()          # [9][2C]
+    da[4] += 1.0                  # RepConv2 = dw3x3(x) + x: the identity rides on the centre tap (one HADD2 less per output)
+    da = da.half()
     parts.append(da.view(torch.uint8).reshape(-1))
     w5 = sd[p + f".body.{3 + k}.conv_1.weight"].float().clone()                            # (C,1,5,5)
     w3 = sd[p + f".body.{3 + k}.conv_2.weight"].float()
     assert w5.shape[1] == 1, "grouped RepConv (Ours+) is not supported by this kernel yet"
     w5[:, :, 1:4, 1:4] += w3
+    w5[:, :, 2, 2] += 1.0         # RepConv = dw5x5 + dw3x3 + x, all merged into one 5x5 kernel per channel
     db = w5.view(C, 25).t().contiguous().half()                                            # [25][C]
     parts.append(db.view(torch.uint8).reshape(-1))
     w2 = sd[p + f".body.{4 + k}.weight"].float().flatten(1)                                # (2C, C)

@@ -115,6 +115,64 @@ def test_conv_mma(env, case):
         assert out[..., cr:].abs().max().item() == 0.0, "padding channels must stay zero"
 
 
+# ------------------------------------------------------------------------------------------------ fused dense CAB body
+DENSE_CASES = [
+    # name, channels, T, H, W, bias      (sizes straddle the 30-wide / 30- or 14-row tiles, incl. a single partial tile)
+    ("c14_ragged", 14, 2, 37, 45, False),
+    ("c14_tiny", 14, 1, 5, 7, False),
+    ("c14_exact_tiles", 14, 1, 60, 60, False),
+    ("c14_bias", 14, 1, 33, 31, True),
+    ("c18_ragged", 18, 2, 23, 41, False),
+    ("c22_bias", 22, 1, 29, 64, True),
+    ("c24_full_width", 24, 1, 16, 35, False),
+]
+
+
+@pytest.mark.parametrize("small", [False, True], ids=["tile30", "tile14"])
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_cab_dense_body(env, case, small):
+    """gsn_cab_dense (conv3x3 -> PReLU -> conv3x3 + channel sums, one kernel) against torch fp32 on the fp16-rounded
+    input, and against the two-launch gsn_conv_mma path."""
+    _, _, eng, _ = env
+    name, c, T, H, W, bias = case
+    if small and c > 16:
+        pytest.skip("the 14-row tile switch only changes the 16-channel instance")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(T, c, H, W, generator=g)
+    key = "testdense." + name
+    w1 = torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5
+    w2 = torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5
+    eng.sd[key + ".body.0.weight"], eng.sd[key + ".body.2.weight"] = w1.to(DEV), w2.to(DEV)
+    eng.sd[key + ".body.1.weight"] = torch.tensor([0.25], device=DEV)
+    b1 = b2 = None
+    if bias:
+        b1, b2 = torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1
+        eng.sd[key + ".body.0.bias"], eng.sd[key + ".body.2.bias"] = b1.to(DEV), b2.to(DEV)
+    xq = x.half().float()
+    mid = F.prelu(F.conv2d(xq, w1.half().float(), b1, padding=1), torch.tensor([0.25]))
+    ref = F.conv2d(mid.half().float(), w2.half().float(), b2, padding=1)     # the kernel keeps the intermediate in fp16
+    xn = to_nhwc(x)
+    os.environ["GSN_CAB_DENSE_SMALL"] = "1" if small else "0"
+    try:
+        r, partial = eng.cab_body_fused(key, xn, c)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("GSN_CAB_DENSE_SMALL", None)
+    got = from_nhwc(r, c)
+    check(got, ref, 2e-3, "cab_dense " + name)
+    cp = xn.shape[3]
+    if cp > c:
+        assert r[..., c:].abs().max().item() == 0.0, "padding channels must stay zero"
+    sums = partial.sum(1)[:, :c].cpu()
+    ref_s = r[..., :c].float().sum((1, 2)).cpu()
+    assert torch.allclose(sums, ref_s, rtol=2e-3, atol=2e-2 * (H * W) ** 0.5), (sums - ref_s).abs().max()
+    # the two-launch path must agree to fp16 rounding
+    r1 = eng.conv(key + ".body.0", [xn], [c], c, prelu_key=key + ".body.1.weight")
+    r2 = eng.conv(key + ".body.2", [r1], [c], c)
+    torch.cuda.synchronize()
+    check(got, from_nhwc(r2, c), 2e-3, "cab_dense vs conv_mma " + name)
+
+
 def test_conv_in_out(env):
     sd, spec, eng, _ = env
     P, L = gio.pkg("host.packing"), gio.pkg("host.lib")

@@ -141,3 +141,25 @@ def test_weight_packing_layouts():
             assert wp[tap, ks, nt, lane, j] == exp
     pc = P.planar_chunks(torch.arange(16 * 24, dtype=torch.float32).view(16, 24))
     assert pc.shape == (3, 16, 8) and pc[2, 5, 3] == 5 * 24 + 2 * 8 + 3
+
+
+@pytest.mark.parametrize("cp,cin", [(16, 14), (24, 18), (24, 22)])
+def test_dense_fragment_packing(cp, cin):
+    """pack_dense_frag (csrc/cab_dense.cu): rebuilding B[k][n] per tap from the per-lane mma fragment words gives the conv
+    weight transposed (k = input channel, n = output channel), zero in the padding rows/columns."""
+    P = gio.pkg("host.packing")
+    w = torch.randn(cin, cin, 3, 3, generator=torch.Generator().manual_seed(3))
+    f = P.pack_dense_frag(w, cp).float().view(9, cp // 8, -1, 32, 2)      # tap, n-tile, word, lane, element
+    k16, k8 = cp // 16, (cp % 16) // 8
+    assert f.shape[2] == 2 * k16 + k8
+    B = torch.zeros(9, cp, cp)
+    for lane in range(32):
+        g_, tig = lane >> 2, lane & 3
+        for nt in range(cp // 8):
+            for wd in range(f.shape[2]):          # words 2s, 2s+1: k = 16s + {0, 8} + 2 tig + e ; tail word: k = 16 k16 + 2 tig + e
+                k0 = 16 * (wd // 2) + 8 * (wd % 2) + 2 * tig if wd < 2 * k16 else 16 * k16 + 2 * tig
+                for e in range(2):
+                    B[:, k0 + e, nt * 8 + g_] = f[:, nt, wd, lane, e]
+    ref = torch.zeros(9, cp, cp)
+    ref[:, :cin, :cin] = w.half().float().reshape(cin, cin, 9).permute(2, 1, 0)
+    assert torch.equal(B, ref)
