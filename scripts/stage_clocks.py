@@ -16,10 +16,9 @@ sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
 eng = gio.pkg("host.engine").Engine(spec, {k: v.cuda() for k, v in sd.items()}, "cuda")
 T, H, W = 20, 360, 640
 x = (0.5 * torch.randn(T, H, W, 64, device="cuda")).half()
-names = {True: ["start", "loads", "gather", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"],
-         False: ["start", "loads", "LN", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]}
-for p, mode, split in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, False),
-                       ("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True),
+names = {True: ["start", "loads", "gather", "in-wait", "LN0", "LN1", "LN2", "LN3", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"],
+         False: ["start", "loads", "in-wait", "LN0", "LN1", "LN2", "LN3", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]}
+for p, mode, split in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True),
                        ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1, False)):
     shift = mode != L.MODE_CAB1
     blob = gio.pkg("host.packing").pack_cab_pass_a(eng.sd, p, 64, shift, 0)

@@ -54,6 +54,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
+// The same descriptor for an operand at a compile-time byte offset from the (128-byte aligned) dynamic shared memory base:
+// the address field just adds (shared addresses are < 2^18, so the 14-bit field never carries into LBO).  One IADD per
+// descriptor for the issuing thread instead of ~10 dependent uniform-datapath ops.
+__device__ __forceinline__ uint64_t smem_desc_at(uint32_t base16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = base16 + (off_bytes >> 4) + ((lbo_bytes >> 4) << 16);
+  const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);   // bit 46: descriptor version 1
+  return ((uint64_t)hi << 32) | lo;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -157,7 +165,7 @@ struct TcCfg {
   static constexpr int P1 = (M1 + 1) * 16, P2 = (M2 + 1) * 16, P3 = (M3 + 1) * 16;
   // shared memory map.  Phase 1: [X | W1 | A1 | R12]; phase 2: [X | G1 ........ | GATED | WT2], A2/Z alias G1.
   static constexpr int S_X = 0;                                      // LN params, conv1 weights, barrier, tmem ptr, sums
-  static constexpr int X_LN = 0, X_C1 = 1024, X_BAR = 1728, X_TMEM = 1744, X_RED = 1792, X_BYTES = 1792 + 16 * 32 * 4;   // X_RED: [16 warps][32] channel-sum partials
+  static constexpr int X_LN = 0, X_C1 = 1024, X_BAR = 1728, X_TMEM = 1744, X_CNT = 1752 /* 4 x u32 arrival counters */, X_BARG = 1768 /* GEMM1 mbarrier */, X_RED = 1792, X_BYTES = 1792 + 16 * 32 * 4;   // X_RED: [16 warps][32] channel-sum partials
   static constexpr int S_W1 = (X_BYTES + 127) / 128 * 128;
   static constexpr int S_A1 = S_W1 + W1_BYTES;
   static constexpr int A1_BYTES = KC1 * P1;
@@ -165,13 +173,18 @@ struct TcCfg {
   static constexpr int R12_BYTES = BOX ? BW * BH * HC * 2 : 0;
   static constexpr int S_G1 = S_W1;
   static constexpr int G1_BYTES = NC * P1;
-  static constexpr int S_GT = ((S_G1 + G1_BYTES > S_R ? S_G1 + G1_BYTES : S_R) + 127) / 128 * 128;
+  static constexpr int IN_BYTES = TMAIN ? (SHIFT ? 3 * M1 * HC * 2 : M1 * C * 2) : 0;    // TMA staging of the LN inputs
+  static constexpr int END1 = S_R + (R12_BYTES > IN_BYTES ? R12_BYTES : IN_BYTES);
+  // CAB1 with TMA staging has room to keep GATED and the phase-2 weights ABOVE the staging area: the next tile's inputs can
+  // then be prefetched as soon as G1 is dead (after the first depthwise stage) instead of after GEMM2, and the phase-2
+  // weights are loaded once per CTA instead of once per tile.  (CAB2's 1.5x wider staging does not leave that room.)
+  static constexpr bool EARLY_PF = TMAIN && !SHIFT;
+  static constexpr int GT_LO = EARLY_PF ? END1 : S_R;
+  static constexpr int S_GT = ((S_G1 + G1_BYTES > GT_LO ? S_G1 + G1_BYTES : GT_LO) + 127) / 128 * 128;
   static constexpr int GT_BYTES = KC2 * P2;
   static constexpr int S_WT2 = (S_GT + GT_BYTES + 127) / 128 * 128;
   static constexpr int END2 = S_WT2 + WT2_BYTES;
-  static constexpr int IN_BYTES = TMAIN ? (SHIFT ? 3 * M1 * HC * 2 : M1 * C * 2) : 0;    // TMA staging of the LN inputs
-  static constexpr int END1 = S_R + (R12_BYTES > IN_BYTES ? R12_BYTES : IN_BYTES);
-  static constexpr bool LATE_WT2 = BOX || TMAIN;   // phase-2 weights go where the box / staging lived: load them later
+  static constexpr bool LATE_WT2 = (BOX || TMAIN) && !EARLY_PF;   // phase-2 weights go where the box / staging lived: load them later
   static constexpr int SMEM = END1 > END2 ? END1 : END2;
   // GEMM2 operand, then the z staging tile.  With TMAIN the kernel is persistent and prefetches the NEXT tile's W1 (at
   // S_W1) and LN inputs (at S_R) while the current tile is in its tail, so A2/z must not sit on W1: it goes 40 KB into
@@ -213,10 +226,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   const unsigned char *wb = reinterpret_cast<const unsigned char *>(d.wblob);
   const size_t frame = (size_t)d.H * d.W * C;
   const uint32_t bar = smem_u32(smem + K::S_X + K::X_BAR);
+  const uint32_t smem16 = smem_u32(smem) >> 4;   // UMMA descriptors address shared memory in 16-byte units
   // debug_stage == 9: thread 0 of every CTA records clock64() at the stage boundaries (profiling aid, tests only)
-  long long *clk = (d.debug_stage == 9 && tid == 0)
-                       ? reinterpret_cast<long long *>(d.debug_out) + (size_t)tile * 16
-                       : nullptr;
+  // (the SECOND tile of a persistent CTA when it has one: steady state, inputs prefetched)
+  long long *clk = nullptr;
+  const bool clk_second = TMAIN && (int)blockIdx.x + (int)gridDim.x < total_tiles;
+  if (d.debug_stage == 9 && tid == 0 && !clk_second) clk = reinterpret_cast<long long *>(d.debug_out) + (size_t)tile * 16;
   int clk_i = 0;
 #define GSN_CLK() do { if (clk && clk_i < 16) clk[clk_i++] = clock64(); } while (0)
   GSN_CLK();
@@ -224,9 +239,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
 
   // ---- P0 (once per CTA): barriers, TMEM, LN params; first tile's loads -------------------------------------------
   const uint32_t bar_in = bar + 8;
+  // GEMM1 hand-off: ln_cnt[m] counts the warps that finished their share of M tile m of A1 (monotonic, 16 per tile); the warp
+  // that arrives last issues that M tile's MMAs and commits them to bar_g1 (MT1 commits per phase).
+  const uint32_t ln_cnt = smem_u32(smem + K::S_X + K::X_CNT), bar_g1 = smem_u32(smem + K::S_X + K::X_BARG);
   if (tid == 32) {
     mbar_init(bar, 1);
     mbar_init(bar_in, 1);
+    mbar_init(bar_g1, K::MT1);
+#pragma unroll
+    for (int m = 0; m < K::MT1; ++m) *reinterpret_cast<volatile uint32_t *>(smem + K::S_X + K::X_CNT + 4 * m) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   const uint32_t tmem = *tmem_slot;
   GSN_CLK();  // 1: loads landed
-  uint32_t in_parity = 0, mma_parity = 0;   // mbarrier phases advance once per completed TMA batch / tcgen05.commit
+  uint32_t in_parity = 0, mma_parity = 0, g1_parity = 0;   // mbarrier phases advance once per TMA batch / tcgen05.commit / tile
   // Prefetch of the next tile's inputs (persistent TMAIN variants), issued once W1 / the staging area of the current tile
   // are dead.
   auto prefetch_next = [&]() {
@@ -397,13 +418,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     const int j = tid & 3;                            // the quad lane never changes across a thread's items
     int chunk_of[NV / 8];
     if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
-    else { chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1; }
+    else {
+      // CAB1: a quad owns one pixel (128 staged bytes).  Lane j takes chunks {j, j+4}, even pixels low chunk first, odd pixels high
+      // chunk first, so the 8 lanes of a quarter warp (2 pixels) hit 8 different 16-byte bank groups in each LDS.128.
+      const int par = (tid >> 2) & 1;               // pixel parity: constant per thread (items advance by 128 pixels)
+      chunk_of[0] = j + 4 * par; chunk_of[1] = j + 4 * (1 - par);
+    }
     float gam[NV], bet[NV];
 #pragma unroll
     for (int k = 0; k < NV / 8; ++k)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { gam[k * 8 + i] = ln_g[chunk_of[k] * 8 + i]; bet[k * 8 + i] = ln_b[chunk_of[k] * 8 + i]; }
+      for (int i = 0; i < 8; i += 4) {
+        const float4 g4 = *reinterpret_cast<const float4 *>(ln_g + chunk_of[k] * 8 + i), b4 = *reinterpret_cast<const float4 *>(ln_b + chunk_of[k] * 8 + i);
+        gam[k * 8 + i] = g4.x; gam[k * 8 + i + 1] = g4.y; gam[k * 8 + i + 2] = g4.z; gam[k * 8 + i + 3] = g4.w;
+        bet[k * 8 + i] = b4.x; bet[k * 8 + i + 1] = b4.y; bet[k * 8 + i + 2] = b4.z; bet[k * 8 + i + 3] = b4.w;
+      }
     if (TMAIN) { mbar_wait(bar_in, in_parity); in_parity ^= 1; }   // the staged LN inputs of this tile have landed
+    GSN_CLK();  // input wait over
     const unsigned char *stg = smem + K::S_R;
     constexpr int PB = (SHIFT && !BOX) ? 2 : NIT;    // items whose loads are in flight together (register budget)
 #pragma unroll
@@ -424,8 +455,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
             raw[it][1] = *reinterpret_cast<const uint4 *>(stg + K::M1 * K::HC * 2 + (size_t)q * K::HC * 2 + j * 16);
             raw[it][(SHIFT && !BOX) ? 2 : 0] = *reinterpret_cast<const uint4 *>(stg + 2 * K::M1 * K::HC * 2 + (size_t)q * K::HC * 2 + j * 16);
           } else {
-            raw[it][0] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + j * 32);
-            raw[it][1] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + j * 32 + 16);
+            raw[it][0] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + chunk_of[0] * 16);
+            raw[it][1] = *reinterpret_cast<const uint4 *>(stg + (size_t)q * C * 2 + chunk_of[1] * 16);
           }
         }
       } else if (inimg) {
@@ -435,8 +466,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
           raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8));
           if (!BOX) raw[it][(SHIFT && !BOX) ? 2 : 0] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(d.hw_pre) + ((size_t)t * d.H * d.W + (size_t)gy * d.W + gx) * K::HC + j * 8));
         } else {
-          raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16));
-          raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8));
+          raw[it][0] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + chunk_of[0] * 8));
+          raw[it][1] = __ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + chunk_of[1] * 8));
         }
       }
     }
@@ -461,9 +492,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
           }
         }
         // one pass: s1 = sum v, s2 = sum v^2 (fp32; |mu| <~ sigma here, so E[v^2] - mu^2 loses nothing that matters in fp16)
-        float s = 0.f, ss = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // 4 independent chains each (latency)
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
+        for (int i = 0; i < NV; ++i) { s4[i & 3] += v[i]; q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]); }
+        float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         ss += __shfl_xor_sync(0xffffffffu, ss, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -487,31 +519,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
           }
         }
       }
-      // M tile `it` of A1 (pixels [128 it, 128 it + 128)) is complete: hand it to the tensor core while the LayerNorm of the
-      // next M tile runs.  GEMM1: D[m] (128 x 2C, TMEM) = A1[m] (128 x CIN) . W1^T
+      // This warp's share of M tile `it` of A1 (pixels [128 it, 128 it + 128)) is complete.  No CTA barrier: every warp bumps
+      // the tile's arrival counter and runs on to the next M tile; whichever warp arrives LAST hands the tile to the tensor
+      // core.  GEMM1: D[m] (128 x 2C, TMEM) = A1[m] (128 x CIN) . W1^T
       fence_async_proxy();   // generic-proxy writes of A1 (and cp.async'd W1) -> visible to the tensor core's async proxy
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        constexpr uint32_t idesc = make_idesc_f16(128, K::N);
-        const uint32_t a_s = smem_u32(smem + K::S_A1), w_s = smem_u32(smem + K::S_W1);
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(ln_cnt + 4 * it) : "memory");
+        if ((old & (kTcThreads / 32 - 1)) == kTcThreads / 32 - 1) {
+          tc_fence_after();
+          constexpr uint32_t idesc = make_idesc_f16(128, K::N);
 #pragma unroll
-        for (int k = 0; k < K::KC1 / 2; ++k) {
-          const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P1 + it * 128 * 16, K::P1, 128);
-          const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
-          umma_f16(tmem + it * K::N, ad, bd, idesc, k > 0);
+          for (int k = 0; k < K::KC1 / 2; ++k) {
+            const uint64_t ad = smem_desc_at(smem16, K::S_A1 + 2 * k * K::P1 + it * 128 * 16, K::P1, 128);
+            const uint64_t bd = smem_desc_at(smem16, K::S_W1 + 2 * k * (K::N * 16), K::N * 16, 128);
+            umma_f16(tmem + it * K::N, ad, bd, idesc, k > 0);
+          }
+          umma_commit(bar_g1);   // tcgen05.commit tracks the issuing thread's MMAs: one commit per M tile, MT1 arrivals per phase
         }
-        if (it == NIT - 1) umma_commit(bar);
       }
+      __syncwarp();
+      GSN_CLK();  // LN iteration `it` done (the last one = LN done)
     }
     }
-    GSN_CLK();  // LN done
-    if (TMAIN) {           // the staging area is dead: stream the phase-2 weights (dw taps + W2) into its place
+    if (TMAIN && K::LATE_WT2) {   // once EVERY warp is done with the staging area, stream the phase-2 weights into its place
+      __syncthreads();
       for (int i = tid; i < K::WT2_BYTES / 16; i += kTcThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
       cp_async_commit();
     }
   }
   if (d.debug_stage == 1) {
+    __syncthreads();
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
                (size_t)tile * K::KC1 * K::M1;
     for (int i = tid; i < K::KC1 * K::M1; i += kTcThreads)
@@ -520,8 +559,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
 
   // ---- P2: GEMM1 was issued M tile by M tile from inside the LayerNorm loop; wait for the last one -----------------
   if (K::LATE_WT2) cp_async_wait<0>();   // phase-2 weights landed (issued after the gather / the LayerNorm)
-  mbar_wait(bar, mma_parity);
-  mma_parity ^= 1;
+  mbar_wait(bar_g1, g1_parity);
+  g1_parity ^= 1;
   tc_fence_after();
   __syncthreads();                 // A1 / W1 are dead from here on; WT2 visible to everyone
   GSN_CLK();  // GEMM1 done
@@ -602,6 +641,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     }
     __syncthreads();
     GSN_CLK();  // dwA done
+    if (K::EARLY_PF) prefetch_next();   // G1 is dead: W1's slot and the staging area are free for the next tile's inputs
   }
   if (d.debug_stage == 2) {
     uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
@@ -707,7 +747,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
       }
     }
     __syncthreads();
-    prefetch_next();       // GATED / A2 reads are done: the staging area and W1 are free for the next tile
+    if (!K::EARLY_PF) prefetch_next();   // GATED / A2 reads are done: the staging area and W1 are free for the next tile
     if (tid < C) {
       d.chan_partial[(size_t)tile * C + tid] = red[tid] + red[C + tid];
     }
@@ -717,13 +757,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   if (tid == 0) {
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_f16(128, K::N);
-    const uint32_t a_s = smem_u32(smem + K::S_A2), w_s = smem_u32(smem + K::S_WT2 + K::DA_BYTES + K::DB_BYTES);
 #pragma unroll
     for (int m = 0; m < K::MT3; ++m)
 #pragma unroll
       for (int k = 0; k < K::KC2 / 2; ++k) {
-        const uint64_t ad = make_smem_desc(a_s + 2 * k * K::P3 + m * 128 * 16, K::P3, 128);
-        const uint64_t bd = make_smem_desc(w_s + 2 * k * (K::N * 16), K::N * 16, 128);
+        const uint64_t ad = smem_desc_at(smem16, K::S_A2 + 2 * k * K::P3 + m * 128 * 16, K::P3, 128);
+        const uint64_t bd = smem_desc_at(smem16, K::S_WT2 + K::DA_BYTES + K::DB_BYTES + 2 * k * (K::N * 16), K::N * 16, 128);
         umma_f16(tmem + m * K::N, ad, bd, idesc, k > 0);
       }
     umma_commit(bar);
@@ -733,7 +772,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   tc_fence_after();
   __syncthreads();                 // A2 is dead: its space becomes the z staging tile
   GSN_CLK();  // GEMM2 done
-  prefetch_next();                 // W1, W2 and the staging area are dead: start the next tile's loads under this tile's tail
+  if (!K::EARLY_PF) prefetch_next();   // W1, W2 and the staging area are dead: start the next tile's loads under this tile's tail
 
   // ---- P7: a * sigmoid(b) (SimpleGate2) -> z tile (fp16 planes) -> coalesced global store; per-tile channel sums --------
   {
@@ -793,7 +832,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
   }
   GSN_CLK();  // stores + sums done
   }   // !MIDCA
-    clk = nullptr;                 // stage clocks are recorded for the first tile of a CTA only
+    clk = nullptr;                 // stage clocks are recorded for one tile of a CTA only
     if (!TMAIN) break;
     tile += (int)gridDim.x;
     if (tile >= total_tiles) break;
@@ -802,6 +841,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cab_pass_a_tc_kernel(const GsnC
     tc_fence_before();
     __syncthreads();               // everyone is done with the previous tile (z staging, TMEM reads, channel sums)
     tc_fence_after();
+    if (d.debug_stage == 9 && tid == 0 && clk_second && tile == (int)blockIdx.x + (int)gridDim.x) {
+      clk = reinterpret_cast<long long *>(d.debug_out) + (size_t)tile * 16;
+      GSN_CLK();   // "start"
+      GSN_CLK();   // "loads" (prefetched during the previous tile)
+    }
   }   // tile loop
   __syncthreads();
   if (warp == 0) {

@@ -162,9 +162,10 @@ class Engine:
         L.check(self.lib.gsn_ca_scale(partial.data_ptr(), partial.shape[1], 1.0 / (H * W), w1.data_ptr(), w2.data_ptr(),
                                       c, w1.shape[0], cp, T, s.data_ptr(), self._stream()), "ca_scale")
         out = self._new(T, H, W, cp)
-        L.check(self.lib.gsn_scale_residual(x.data_ptr(), r2.data_ptr(), s.data_ptr(),
-                                            extra.data_ptr() if extra is not None else None, out.data_ptr(), T, H * W, cp,
-                                            self._stream()), "scale_residual")
+        with self._timed(f"scale_residual[{cp} {H}x{W}]" if self.timeline_detail else "scale_residual", T * H * W):
+            L.check(self.lib.gsn_scale_residual(x.data_ptr(), r2.data_ptr(), s.data_ptr(),
+                                                extra.data_ptr() if extra is not None else None, out.data_ptr(), T, H * W, cp,
+                                                self._stream()), "scale_residual")
         return out
 
     def seq_cabs(self, p, x, c):
@@ -219,7 +220,7 @@ class Engine:
         b = L.CabPassB()
         b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
-        with self._timed("cab_pass_b", T * H * W):
+        with self._timed(f"cab_pass_b[{H}x{W}]" if self.timeline_detail else "cab_pass_b", T * H * W):
             L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
         return out
 
@@ -316,7 +317,7 @@ class Engine:
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
             a.debug_stage, a.debug_out = debug_stage, dbg.data_ptr()
-        with self._timed("cab_pass_a_shift" if shift else "cab_pass_a", T * H * W):
+        with self._timed(("cab_pass_a_shift" if shift else "cab_pass_a") + (f"[{H}x{W}]" if self.timeline_detail else ""), T * H * W):
             L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
         if self.spec.denoise:
             # z holds u = RepConv(gate); finish the block: mid CALayer2 folded into W2, then 1x1 + sigmoid gate
