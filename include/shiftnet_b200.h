@@ -147,10 +147,20 @@ typedef struct {
                            per-tile sums of the gated tensor; gsn_cab_fold_mid + gsn_cab_pass_a2 finish the block. */
   const void *hw_pre;   /* CAB2 modes: NULL = the shift gather + conv1 run inside pass A (bounding box in smem);
                            non-NULL = (T,H,W,C/2) fp16 from gsn_shift_conv1, read in the LayerNorm load stage */
+  const void *a1_pre;   /* NULL = the LayerNorm (d2:209,250) runs inside pass A.  non-NULL = its output, precomputed by
+                           gsn_ln_planar in the k-chunk planar layout [T][CIN/8][H][W][8] fp16 (CIN = C for CAB1, 3C/2 for
+                           CAB2): pass A lands each tile's halo'd region with one TMA tile load directly in the tensor-core
+                           operand layout (cab_pass_a_pre.cu); x and hw_pre are not read then. */
 } GsnCabPassA;
 
 int gsn_cab_tiles(int mode, int H, int W);
 int gsn_cab_pass_a(const GsnCabPassA *d, void *stream);
+
+/* LayerNorm2d of CAB1 / CAB2 (d2:19-28,44-53,209,250) as its own HBM-bound kernel, for GsnCabPassA.a1_pre:
+ * a1[t][chunk][y][x][8] = LN([rolled stream | hw_pre])  (CAB1: LN(x)); x (T,H,W,C) fp16, hw_pre (T,H,W,C/2) fp16 from
+ * gsn_shift_conv1 (CAB2 modes), ln = fp32 gamma[CIN] then beta[CIN]; C = 64. */
+int gsn_ln_planar(const void *x, const void *hw_pre, int T, int H, int W, int C, int mode, int circular, const float *ln,
+                  void *a1, void *stream);
 
 /* Grouped spatial-temporal shift folded into the load stage of conv1 (dw3x3): out = conv1(spatial_shift2(hw)) with hw the
  * neighbour frame's half of the channels (d2:465-519, 226,254); out (T,H,W,C/2) fp16.  wc1: fp16 [9][C/2]. */

@@ -18,8 +18,11 @@ T, H, W = 20, 360, 640
 x = (0.5 * torch.randn(T, H, W, 64, device="cuda")).half()
 names = {True: ["start", "loads", "gather", "in-wait", "LN0", "LN1", "LN2", "LN3", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"],
          False: ["start", "loads", "in-wait", "LN0", "LN1", "LN2", "LN3", "GEMM1", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]}
-for p, mode, split in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True),
-                       ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1, False)):
+PRE_NAMES = ["start", "GEMM1-wait", "tmem->G1", "dwA", "dwB", "GEMM2", "gate2", "store+sums"]
+for p, mode, split, pre in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True, True),
+                            ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1, False, True),
+                            ("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FWD, True, False),
+                            ("stage1.encoder_level1.encoder_level1.1", L.MODE_CAB1, False, False)):
     shift = mode != L.MODE_CAB1
     blob = gio.pkg("host.packing").pack_cab_pass_a(eng.sd, p, 64, shift, 0)
     nt = eng.lib.gsn_cab_tiles(mode, H, W)
@@ -35,15 +38,20 @@ for p, mode, split in (("stage1.encoder_level1.encoder_level1.0", L.MODE_CAB2_FW
         hw_pre = torch.empty(T, H, W, 32, dtype=torch.float16, device="cuda")
         L.check(eng.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, 64, mode, 1, wc1.data_ptr(), hw_pre.data_ptr(), eng._stream()))
         a.hw_pre = hw_pre.data_ptr()
+    if pre:
+        ln = torch.cat((eng.sd[p + ".norm.weight"].float(), eng.sd[p + ".norm.bias"].float())).contiguous()
+        a1 = torch.empty(T, 12 if shift else 8, H, W, 8, dtype=torch.float16, device="cuda")
+        L.check(eng.lib.gsn_ln_planar(x.data_ptr(), a.hw_pre, T, H, W, 64, mode, 1, ln.data_ptr(), a1.data_ptr(), eng._stream()))
+        a.a1_pre = a1.data_ptr()
     for _ in range(2):
         L.check(eng.lib.gsn_cab_pass_a(C.byref(a), eng._stream()))
     torch.cuda.synchronize()
     c = dbg.view(T * nt, 16).double()
     c = c[c[:, 0] > 0]          # persistent kernel: only the first tile of every CTA records its clocks
-    nm = names[shift and not split]
+    nm = PRE_NAMES if pre else names[shift and not split]
     n = len(nm)
     d = (c[:, 1:n] - c[:, :n - 1])
     tot = (c[:, n - 1] - c[:, 0])
-    print(f"mode={'shift' if shift else 'cab1'} split={split} tiles={T*nt} recorded={c.shape[0]} mean cycles/tile={tot.mean().item():.0f} (min {tot.min().item():.0f} max {tot.max().item():.0f})")
+    print(f"mode={'shift' if shift else 'cab1'} pre={pre} split={split} tiles={T*nt} recorded={c.shape[0]} mean cycles/tile={tot.mean().item():.0f} (min {tot.min().item():.0f} max {tot.max().item():.0f})")
     for i in range(n - 1):
         print(f"   {nm[i+1]:12s} {d[:, i].mean().item():8.0f}  ({100 * d[:, i].mean().item() / tot.mean().item():4.1f}%)")

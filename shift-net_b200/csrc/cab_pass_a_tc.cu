@@ -15,120 +15,11 @@
 
 #include "common.cuh"
 #include "shift_common.cuh"
+#include "tc_common.cuh"
 
 namespace gsn {
 
 constexpr int kTcThreads = 512;
-
-// ---- tcgen05 / mbarrier wrappers ------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  int spin = 0;
-  do {
-    if (++spin > (1 << 26)) __trap();   // a lost TMA / MMA completion must fault, not hang the GPU
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-
-// K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// element (row r, k) lives at start + (r%8)*16 + (r/8)*SBO + (k%8)*2 + (k/8)*LBO   [bytes]
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
-  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
-// The same descriptor for an operand at a compile-time byte offset from the (128-byte aligned) dynamic shared memory base:
-// the address field just adds (shared addresses are < 2^18, so the 14-bit field never carries into LBO).  One IADD per
-// descriptor for the issuing thread instead of ~10 dependent uniform-datapath ops.
-__device__ __forceinline__ uint64_t smem_desc_at(uint32_t base16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  const uint32_t lo = base16 + (off_bytes >> 4) + ((lbo_bytes >> 4) << 16);
-  const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);   // bit 46: descriptor version 1
-  return ((uint64_t)hi << 32) | lo;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-// sigmoid(x) = 0.5 tanh(x/2) + 0.5 with the single-MUFU tanh.approx (rel. error 2^-11, i.e. below the fp16 rounding of z);
-// the exp+rcp form costs two MUFU ops per element and made the gate stage SFU-bound (2048 of 2350 cycles per tile).
-__device__ __forceinline__ float sigmoid_tanh(float x) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return fmaf(t, 0.5f, 0.5f);
-}
-
-// ---- packed half helpers --------------------------------------------------------------------------
-struct H8 {
-  __half2 h[4];
-};
-__device__ __forceinline__ H8 lds_h8(const unsigned char *p) {
-  const uint4 v = *reinterpret_cast<const uint4 *>(p);
-  H8 r;
-  r.h[0] = *reinterpret_cast<const __half2 *>(&v.x);
-  r.h[1] = *reinterpret_cast<const __half2 *>(&v.y);
-  r.h[2] = *reinterpret_cast<const __half2 *>(&v.z);
-  r.h[3] = *reinterpret_cast<const __half2 *>(&v.w);
-  return r;
-}
-__device__ __forceinline__ void sts_h8(unsigned char *p, const H8 &a) {
-  uint4 v;
-  v.x = *reinterpret_cast<const uint32_t *>(&a.h[0]);
-  v.y = *reinterpret_cast<const uint32_t *>(&a.h[1]);
-  v.z = *reinterpret_cast<const uint32_t *>(&a.h[2]);
-  v.w = *reinterpret_cast<const uint32_t *>(&a.h[3]);
-  *reinterpret_cast<uint4 *>(p) = v;
-}
-__device__ __forceinline__ void h8_fma(H8 &acc, const H8 &a, const H8 &w) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc.h[i] = __hfma2(a.h[i], w.h[i], acc.h[i]);
-}
-__device__ __forceinline__ void h8_mul(H8 &acc, const H8 &a, const H8 &w) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc.h[i] = __hmul2(a.h[i], w.h[i]);
-}
 
 // ---- configuration ----------------------------------------------------------------------------------
 // SHIFT: CAB2 (LayerNorm input = [rolled stream | conv1(shifted half)]).  BOX: the gather runs inside this kernel (bounding

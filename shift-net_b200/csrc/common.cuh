@@ -16,6 +16,10 @@ void count_launch();
 int check_launch(const char *what);   // cudaGetLastError -> GSN_E_CUDA + message
 // 4-D fp16 NHWC tensor map (dims innermost first: C, W, H, T) with a (bc, bw, bh, 1) box, zero OOB fill. false = unavailable.
 bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh);
+// 4-D fp16 tensor map over a k-chunk planar tensor [T][KC][H][W][8] (dims innermost first: W*8, H, KC, T) with a
+// (bw*8, bh, KC, 1) box: the box lands in shared memory as KC planes of bh*bw 16-byte pixel vectors = the no-swizzle
+// K-major UMMA operand layout.  Zero OOB fill.
+bool encode_tmap_planar(CUtensorMap *tm, const void *base, int W, int H, int KC, int T, int bw, int bh);
 
 #define GSN_REQUIRE(cond, ...)             \
   do {                                     \

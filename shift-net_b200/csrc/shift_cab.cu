@@ -622,6 +622,7 @@ static int launch_pass_a(const GsnCabPassA &d, cudaStream_t st) {
 constexpr int kTileH_Cab1 = 16, kTileH_Cab2 = 8;
 
 int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st);  // cab_pass_a_tc.cu
+int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
 
 // GSN_PASS_A_LEGACY=1 selects the mma.sync cross-check implementation of pass A (tests / bisecting only).
 static bool use_legacy_pass_a() {
@@ -645,6 +646,7 @@ extern "C" int gsn_cab_pass_a(const GsnCabPassA *dp, void *stream) {
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_a: mode=%d", d.mode);
   GSN_REQUIRE(d.debug_stage == 0 || d.debug_out, "cab_pass_a: debug_stage without debug_out");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d.a1_pre) return cab_pass_a_pre_dispatch(d, st);     // LayerNorm'd operand precomputed (gsn_ln_planar)
   if (!use_legacy_pass_a() || d.mid_ca) return cab_pass_a_tc_dispatch(d, st);
   if (d.C == 64) {
     if (d.mode == GSN_MODE_CAB1) return launch_pass_a<64, false, kTileH_Cab1>(d, st);

@@ -31,6 +31,9 @@ class Engine:
         # shifted+conv1'd half (C/2 channels) and pass A reads it in its LayerNorm load stage.
         import os
         self.shift_split = os.environ.get("GSN_SHIFT_SPLIT", "1") == "1"
+        # LayerNorm of CAB1/CAB2 as its own HBM-bound kernel writing the k-chunk planar operand that pass A lands by TMA
+        # directly in the tensor-core layout (csrc/cab_pass_a_pre.cu); GSN_PASS_A_PRE=0 keeps the LayerNorm inside pass A
+        self.pass_a_pre = os.environ.get("GSN_PASS_A_PRE", "1") == "1" and self.shift_split
         # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
         self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"
         # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
@@ -313,6 +316,15 @@ class Engine:
                 L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, a.circular, self.cache[ckw].data_ptr(),
                                                  hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
             a.hw_pre = hw_pre.data_ptr()
+        if self.pass_a_pre:
+            ckl = ("ln", p)
+            if ckl not in self.cache:
+                self.cache[ckl] = torch.cat((self.sd[p + ".norm.weight"].float(), self.sd[p + ".norm.bias"].float())).contiguous()
+            a1 = self._new(T, 12 if shift else 8, H, W, 8)
+            with self._timed("ln_planar", T * H * W):
+                L.check(self.lib.gsn_ln_planar(x.data_ptr(), a.hw_pre, T, H, W, Cc, mode, a.circular, self.cache[ckl].data_ptr(),
+                                               a1.data_ptr(), self._stream()), "ln_planar " + p)
+            a.a1_pre = a1.data_ptr()
         dbg = None
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
