@@ -41,16 +41,17 @@ static TmapEncodeFn tmap_encoder() {
   return enc;
 }
 
-bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh) {
+bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh, bool swizzle128) {
   TmapEncodeFn enc = tmap_encoder();
   if (!enc || (long long)C * 2 % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  if (swizzle128 && bc * 2 != 128) return false;   // the 128-byte swizzle spans exactly one box row
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool encode_tmap_planar(CUtensorMap *tm, const void *base, int W, int H, int KC, int T, int bw, int bh) {

@@ -52,14 +52,17 @@ struct PreCfg {
   static constexpr int S_A1 = S_A2 + A2_BYTES;                        // TMA destination = GEMM1 operand of the NEXT tile
   static constexpr int A1_BYTES = KC1 * PA1;
   static constexpr int LO_END = (S_G1 + G1_BYTES > S_A1 + A1_BYTES ? S_G1 + G1_BYTES : S_A1 + A1_BYTES);
-  static constexpr int S_GT = (LO_END + 127) / 128 * 128;
+  static constexpr int S_GT = (LO_END + 1023) / 1024 * 1024;
   static constexpr int GT_BYTES = KC2 * P2;
-  static constexpr int S_Z = S_GT;                                    // z staging tile (GATED is dead after the dw5x5)
+  // z staging tile (GATED is dead after the dw5x5): 256 pixels x 128 bytes, pixel-major with the 128-byte TMA swizzle
+  // (16-byte chunk c of pixel p sits at chunk c ^ (p & 7): lane = pixel writes are bank-conflict free) -> ONE TMA tile store
+  static constexpr int S_Z = S_GT;
+  static constexpr int Z_BYTES = M3 * C * 2;
   static constexpr int S_WT2 = (S_GT + GT_BYTES + 127) / 128 * 128;
   static constexpr int S_W1 = (S_WT2 + WT2_BYTES + 127) / 128 * 128;
   static constexpr int SMEM = S_W1 + W1_BYTES;
   static_assert(S_A1 % 128 == 0, "TMA destination alignment");
-  static_assert(A2_BYTES <= GT_BYTES, "z staging fits the GATED area");
+  static_assert(Z_BYTES <= GT_BYTES && S_Z % 1024 == 0, "z staging fits the GATED area, swizzle-atom aligned");
   static_assert(S_A1 + (KC1 - 1) * PA1 + MT1 * 128 * 16 <= SMEM, "UMMA rows beyond M1 stay inside the allocation");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -79,10 +82,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 
 template <int KC1, bool MIDCA>
-__global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const GsnCabPassA d, const __grid_constant__ CUtensorMap tm_a1) {
+__global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const GsnCabPassA d, const __grid_constant__ CUtensorMap tm_a1,
+                                                                       const __grid_constant__ CUtensorMap tm_z) {
   using K = PreCfg<KC1>;
   constexpr int C = K::C;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // persistent CTAs: linear tile index = (frame * tiles_y + tile_y) * tiles_x + tile_x, stride gridDim.x
   const int tiles_x = (d.W + K::TW - 1) / K::TW, tiles_y = (d.H + K::TH - 1) / K::TH;
@@ -117,6 +121,9 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
         "r"(bar_in)
         : "memory");
   };
+  // Single-thread roles are spread over four warps so that no warp carries all the issue latency:
+  //   thread 0: GEMM2 and the A1 TMA load; kIssA: next tile's GEMM1 M tiles 2,3; kIssB: M tiles 0,1; kIssZ: the z TMA store
+  constexpr int kIssA = 128, kIssB = 256, kIssZ = 384;
   uint32_t tmem = 0;
   // GEMM1 of M tiles [m0, m1): D[m] (128 x 2C fp32, TMEM columns [m*N, m*N + N)) = A1[m] (128 x CIN) . W1^T; one commit
   auto issue_gemm1 = [&](int m0, int m1) {
@@ -153,13 +160,15 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
   __syncthreads();
   tc_fence_after();
   tmem = *tmem_slot;
-  uint32_t in_parity = 0, mma_parity = 0, g1_parity = 0;   // in_parity is only ever used by thread 0
+  // mbarrier phases: bar_in completes once per A1 load, bar_g1 once per tile (two commits), bar_mma once per GEMM2; every
+  // thread tracks all three parities (the waiters of bar_in are the issuing threads only)
+  uint32_t in_parity = 0, mma_parity = 0, g1_parity = 0;
   if (tid == 0) {
     mbar_wait(bar_in, in_parity);
-    in_parity ^= 1;
     issue_gemm1(2, 4);
     issue_gemm1(0, 2);
   }
+  in_parity ^= 1;
 
   for (;;) {   // ---- tile loop ----
   if (d.debug_stage == 9 && tid == 0 && (clk_second ? tile == (int)blockIdx.x + (int)gridDim.x : true))
@@ -202,6 +211,7 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
         }
       }
     }
+    if (!MIDCA && tid == kIssZ) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // previous z tile left smem
     tc_fence_before();
     __syncthreads();   // G1 complete; every thread is done with the previous tile's z staging / channel sums
     GSN_CLK();  // 2: TMEM -> G1 done
@@ -364,10 +374,9 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
     }
     tc_fence_before();
     __syncthreads();       // A2 / GATED reads are done
-    if (has_next && tid == 0) {   // TMEM is idle since the drain: the whole GEMM1 of the next tile
+    if (has_next && tid == kIssA) {   // TMEM is idle since the drain: the whole GEMM1 of the next tile
       tc_fence_after();
       mbar_wait(bar_in, in_parity);
-      in_parity ^= 1;
       issue_gemm1(2, 4);
       issue_gemm1(0, 2);
     }
@@ -376,7 +385,6 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
   } else {
 
   // ---- P6: GEMM2 on the tensor core: (256 x C) . W2^T -> TMEM columns [0, 2*N); then the next tile's M tiles 2,3 ------
-  bool early = false;
   if (tid == 0) {
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_f16(128, K::N);
@@ -389,12 +397,12 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
         umma_f16(tmem + m * K::N, ad, bd, idesc, k > 0);
       }
     umma_commit(bar_mma);
-    // TMEM columns [2N, 4N) were drained in P3: if the next tile's A1 has landed, its M tiles 2,3 can run right behind GEMM2
-    if (has_next && mbar_test(bar_in, in_parity)) {
-      in_parity ^= 1;
-      issue_gemm1(2, 4);
-      early = true;
-    }
+  } else if (has_next && tid == kIssA) {
+    // TMEM columns [2N, 4N) were drained in P3: the next tile's M tiles 2,3 run right behind GEMM2 (its A1 was requested
+    // before the dw5x5 stage)
+    tc_fence_after();
+    mbar_wait(bar_in, in_parity);
+    issue_gemm1(2, 4);
   }
   mbar_wait(bar_mma, mma_parity);
   mma_parity ^= 1;
@@ -418,8 +426,8 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
 #pragma unroll
       for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(a[i]) * sigmoid_tanh(__uint_as_float(b[i]));
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4)
-        *reinterpret_cast<uint4 *>(smem + K::S_Z + (cg * 4 + c4) * K::P3 + px * 16) = pack8(*reinterpret_cast<float(*)[8]>(&z[c4 * 8]));
+      for (int c4 = 0; c4 < 4; ++c4)   // pixel-major 128-byte rows, 16-byte chunks XOR-swizzled with the pixel index (TMA SWIZZLE_128B)
+        *reinterpret_cast<uint4 *>(smem + K::S_Z + px * 128 + (((cg * 4 + c4) ^ (px & 7)) << 4)) = pack8(*reinterpret_cast<float(*)[8]>(&z[c4 * 8]));
       // sum over the warp's 32 pixels of each of its 32 channels: butterfly that halves the live values per step;
       // lane l ends up with channel cg*32 + l (fixed order => deterministic)
       if (!valid) {
@@ -437,25 +445,20 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
       }
       red[warp * 32 + lane] = z[0];
     }
+    fence_async_proxy();   // staging writes -> visible to the TMA store
     tc_fence_before();
     __syncthreads();
     GSN_CLK();  // 6: gate2 -> z tile done
-    // TMEM columns [0, 2N) are free again: the rest of the next tile's GEMM1 runs under the store phase
-    if (has_next && tid == 0) {
+    if (tid == kIssZ) {    // z tile -> HBM: one TMA tile store (pixels beyond the image border are clipped by the hardware)
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::
+                       "l"(reinterpret_cast<uint64_t>(&tm_z)), "r"(0), "r"(x0), "r"(y0), "r"(t), "r"(smem_u32(smem + K::S_Z))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    } else if (has_next && tid == kIssB) {
+      // TMEM columns [0, 2N) are free again: the rest of the next tile's GEMM1 runs under the tail of this tile
       tc_fence_after();
-      if (!early) {
-        mbar_wait(bar_in, in_parity);
-        in_parity ^= 1;
-        issue_gemm1(2, 4);
-      }
+      mbar_wait(bar_in, in_parity);
       issue_gemm1(0, 2);
-    }
-    __half *zg = reinterpret_cast<__half *>(d.z) + (size_t)t * frame;
-    for (int i = tid; i < K::M3 * K::KC2; i += kPreThreads) {
-      const int ch = i % K::KC2, p = i / K::KC2;
-      const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
-      if (gy < d.H && gx < d.W)
-        *reinterpret_cast<uint4 *>(zg + ((size_t)gy * d.W + gx) * C + ch * 8) = *reinterpret_cast<const uint4 *>(smem + K::S_Z + ch * K::P3 + p * 16);
     }
     if (tid < C) {   // channel tid = group cg, lane l: the 8 warps (4 lane quarters x 2 M tiles) that own the group
       const int cg = tid >> 5, l = tid & 31;
@@ -471,10 +474,12 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
   }   // !MIDCA
     clk = nullptr;
     if (!has_next) break;
+    in_parity ^= 1;
     tile = nt;
     t = nt_t; x0 = nt_x0; y0 = nt_y0;
   }   // tile loop
 #undef GSN_CLK
+  if (tid == kIssZ) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(256) ln_planar_kernel(const __half *__restrict
 }
 
 template <int KC1, bool MIDCA>
-static int launch_pass_a_pre(const GsnCabPassA &d, cudaStream_t st, const CUtensorMap &tm) {
+static int launch_pass_a_pre(const GsnCabPassA &d, cudaStream_t st, const CUtensorMap &tm, const CUtensorMap &tm_z) {
   using K = PreCfg<KC1>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -557,7 +562,7 @@ static int launch_pass_a_pre(const GsnCabPassA &d, cudaStream_t st, const CUtens
     if (num_sms <= 0) num_sms = 148;
   }
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
-  cab_pass_a_pre_kernel<KC1, MIDCA><<<grid, kPreThreads, K::SMEM, st>>>(d, tm);
+  cab_pass_a_pre_kernel<KC1, MIDCA><<<grid, kPreThreads, K::SMEM, st>>>(d, tm, tm_z);
   count_launch();
   return check_launch("cab_pass_a_pre");
 }
@@ -575,8 +580,14 @@ int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st) {
     set_error("cab_pass_a (a1_pre): cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", d.W, d.H, d.T);
     return GSN_E_CUDA;
   }
-  if (shift) return d.mid_ca ? launch_pass_a_pre<12, true>(d, st, tm) : launch_pass_a_pre<12, false>(d, st, tm);
-  return d.mid_ca ? launch_pass_a_pre<8, true>(d, st, tm) : launch_pass_a_pre<8, false>(d, st, tm);
+  CUtensorMap tm_z;     // z (T,H,W,64) NHWC, one 16x16-pixel tile per store, 128-byte swizzle
+  memset(&tm_z, 0, sizeof(tm_z));
+  if (!d.mid_ca && !encode_tmap_nhwc(&tm_z, d.z, 64, d.W, d.H, d.T, 64, 16, 16, true)) {
+    set_error("cab_pass_a (a1_pre): cuTensorMapEncodeTiled(z) failed (W=%d H=%d T=%d)", d.W, d.H, d.T);
+    return GSN_E_CUDA;
+  }
+  if (shift) return d.mid_ca ? launch_pass_a_pre<12, true>(d, st, tm, tm_z) : launch_pass_a_pre<12, false>(d, st, tm, tm_z);
+  return d.mid_ca ? launch_pass_a_pre<8, true>(d, st, tm, tm_z) : launch_pass_a_pre<8, false>(d, st, tm, tm_z);
 }
 
 }  // namespace gsn

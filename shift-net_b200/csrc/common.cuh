@@ -15,7 +15,8 @@ void set_error(const char *fmt, ...);
 void count_launch();
 int check_launch(const char *what);   // cudaGetLastError -> GSN_E_CUDA + message
 // 4-D fp16 NHWC tensor map (dims innermost first: C, W, H, T) with a (bc, bw, bh, 1) box, zero OOB fill. false = unavailable.
-bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh);
+// swizzle128: CU_TENSOR_MAP_SWIZZLE_128B (box rows of exactly 128 bytes; 16-byte chunk c of box row r sits at chunk c ^ (r & 7)).
+bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, int T, int bc, int bw, int bh, bool swizzle128 = false);
 // 4-D fp16 tensor map over a k-chunk planar tensor [T][KC][H][W][8] (dims innermost first: W*8, H, KC, T) with a
 // (bw*8, bh, KC, 1) box: the box lands in shared memory as KC planes of bh*bw 16-byte pixel vectors = the no-swizzle
 // K-major UMMA operand layout.  Zero OOB fill.
