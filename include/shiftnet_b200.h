@@ -165,6 +165,11 @@ int gsn_ln_planar(const void *x, const void *hw_pre, int T, int H, int W, int C,
 /* Grouped spatial-temporal shift folded into the load stage of conv1 (dw3x3): out = conv1(spatial_shift2(hw)) with hw the
  * neighbour frame's half of the channels (d2:465-519, 226,254); out (T,H,W,C/2) fp16.  wc1: fp16 [9][C/2]. */
 int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, void *out, void *stream);
+/* The same gather + conv1, followed in the same kernel by CAB2's LayerNorm over [rolled stream | conv1 output] (d2:250-254):
+ * a1 = k-chunk planar [T][3C/16][H][W][8] fp16 for GsnCabPassA.a1_pre (the conv1 output never goes to HBM).  C = 64.
+ * ln: fp32 gamma[3C/2], beta[3C/2]. */
+int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
+                       void *a1, void *stream);
 
 /* mid fold (denoise): w2eff[t] = W2 diag(s1_t) as fp16 [T][C/8][2C][8], s1 from the mid CALayer2 on mean(gated).
  * w_du0 [cr][C], w_du2 [C][cr], w2 [2C][C] (fp32). */
@@ -192,6 +197,9 @@ typedef struct {
   const void *weff;     /* from gsn_cab_fold */
   const float *beff;
   void *out;            /* (T,H,W,C) fp16 */
+  const float *ln_next; /* optional (C = 64): fp32 gamma[C], beta[C] of the LayerNorm that consumes `out` next (CAB1.norm) */
+  void *a1_next;        /* optional: that LayerNorm applied to `out`, k-chunk planar [T][C/8][H][W][8] fp16 (see
+                           GsnCabPassA.a1_pre) -- saves the separate gsn_ln_planar pass over `out` */
 } GsnCabPassB;
 
 int gsn_cab_pass_b(const GsnCabPassB *d, void *stream);

@@ -67,20 +67,6 @@ struct PreCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
 template <int KC1, bool MIDCA>
 __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const GsnCabPassA d, const __grid_constant__ CUtensorMap tm_a1,
                                                                        const __grid_constant__ CUtensorMap tm_z) {
@@ -146,6 +132,12 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  // Equal tiles keep the 148 persistent CTAs in lockstep, so all their A1 loads (60-90 KB each) would hit HBM in the same
+  // instant and arrive late; a one-off start skew of a quarter tile per CTA (mod 4) spreads them for the whole launch.
+  if (d.debug_stage != 8 && (blockIdx.x & 3)) {
+    const long long until = clock64() + (long long)(blockIdx.x & 3) * 4096;
+    while (clock64() < until) { }
+  }
   if (tid == 0) issue_a1(t, x0, y0);
   for (int i = tid; i < K::W1_BYTES / 16; i += kPreThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
   for (int i = tid; i < K::WT2_BYTES / 16; i += kPreThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);
@@ -420,6 +412,21 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
       const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32;
       tmem_ld32(base, a);
       tmem_ld32(base + C, b);
+      // Both halves of GEMM2's output now sit in registers: TMEM columns [0, 2N) are free again.  Every warp signals that on
+      // named barrier 1 without waiting; only the warp of thread kIssB waits for all 16 and then issues the rest of the next
+      // tile's GEMM1 (M tiles 0,1), which runs under the sigmoid gate and the store.
+      tc_fence_before();
+      if (has_next && warp == kIssB / 32) {
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kPreThreads) : "memory");
+        if (tid == kIssB) {
+          tc_fence_after();
+          mbar_wait(bar_in, in_parity);
+          issue_gemm1(0, 2);
+        }
+        __syncwarp();
+      } else if (has_next) {
+        asm volatile("bar.arrive 1, %0;\n" ::"n"(kPreThreads) : "memory");
+      }
       const int px = m * 128 + quarter * 32 + lane;
       const bool valid = (y0 + px / K::TW < d.H) && (x0 + px % K::TW < d.W);
       float z[32];
@@ -454,11 +461,6 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
                        "l"(reinterpret_cast<uint64_t>(&tm_z)), "r"(0), "r"(x0), "r"(y0), "r"(t), "r"(smem_u32(smem + K::S_Z))
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-    } else if (has_next && tid == kIssB) {
-      // TMEM columns [0, 2N) are free again: the rest of the next tile's GEMM1 runs under the tail of this tile
-      tc_fence_after();
-      mbar_wait(bar_in, in_parity);
-      issue_gemm1(0, 2);
     }
     if (tid < C) {   // channel tid = group cg, lane l: the 8 warps (4 lane quarters x 2 M tiles) that own the group
       const int cg = tid >> 5, l = tid & 31;

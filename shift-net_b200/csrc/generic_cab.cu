@@ -364,10 +364,14 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
 // 16x16-pixel tiles, the 34x34x(C/2) source box staged with zero-filling cp.async, per-channel sliding windows,
 // results staged in smem and written with 16-byte stores.  Memory/L2 bound; 2 CTAs per SM overlap load and compute.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, bool TMA>
+// LN (C = 64): CAB2's LayerNorm over [rolled stream | conv1 output] (gshift_deblur2.py:250-254) runs in the same kernel and the
+// result leaves in the k-chunk planar layout [T][12][H][W][8] of GsnCabPassA.a1_pre; `out` then holds that tensor and the conv1
+// output never goes to HBM.
+template <int C, bool TMA, bool LN = false>
 __global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(const __half *__restrict__ x, int T, int H, int W, int mode,
                                                              int circular, const __half *__restrict__ wc1,
-                                                             __half *__restrict__ out, const __grid_constant__ CUtensorMap tmap) {
+                                                             __half *__restrict__ out, const __grid_constant__ CUtensorMap tmap,
+                                                             const float *__restrict__ ln = nullptr) {
   constexpr int HC = C / 2, CH = HC / 8, TS = 16, BW = TS + 18;
   extern __shared__ __align__(128) unsigned char smem[];
   __half *box = reinterpret_cast<__half *>(smem);                       // [BW*BW][HC]
@@ -376,6 +380,23 @@ __global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(con
   const int t = blockIdx.z, x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
   const RollSrc rs = roll_source(mode, circular, t, T, C);
   const bool fwd = mode == GSN_MODE_CAB2_FWD;
+  // LN: a quad of lanes owns a pixel (4 pixels per thread); the rolled stream of those pixels is requested now and consumed
+  // after the conv (its latency hides under the TMA wait and the conv loop)
+  uint4 rolled[LN ? 4 : 1][2];
+  if (LN) {
+    const int j = tid & 3;
+    const size_t frame = (size_t)H * W * C;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int p = (tid >> 2) + it * 64, gy = y0 + p / TS, gx = x0 + p % TS;
+      rolled[it][0] = rolled[it][1] = make_uint4(0, 0, 0, 0);
+      if (gy < H && gx < W) {
+        const size_t pix = ((size_t)gy * W + gx) * C;
+        rolled[it][0] = __ldg(reinterpret_cast<const uint4 *>(x + rs.f_lo * frame + pix + rs.c_lo + j * 8));
+        rolled[it][1] = __ldg(reinterpret_cast<const uint4 *>(x + rs.f_hi * frame + pix + rs.c_hi + j * 8));
+      }
+    }
+  }
   if (TMA) {
     // One TMA tile load brings the whole 34x34x(C/2) box (out-of-image elements are zero-filled by the hardware).
     __shared__ __align__(8) unsigned long long bar;
@@ -455,6 +476,44 @@ __global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(con
     }
   }
   __syncthreads();
+  if (LN) {
+    constexpr int CIN = C + HC, KC = CIN / 8;
+    const int j = tid & 3;
+    const size_t hw = (size_t)H * W;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int p = (tid >> 2) + it * 64, gy = y0 + p / TS, gx = x0 + p % TS;
+      float v[24];
+      unpack8(rolled[it][0], *reinterpret_cast<float(*)[8]>(&v[0]));
+      unpack8(rolled[it][1], *reinterpret_cast<float(*)[8]>(&v[8]));
+      unpack8(*reinterpret_cast<const uint4 *>(ot + (size_t)p * HC + j * 8), *reinterpret_cast<float(*)[8]>(&v[16]));
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 24; ++i) { s4[i & 3] += v[i]; q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]); }
+      float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      const float mu = s * (1.f / CIN);
+      const float rstd = rsqrtf(fmaxf(ss * (1.f / CIN) - mu * mu, 0.f) + 1e-6f);
+      const float nmr = -mu * rstd;
+      if (gy < H && gx < W) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int ch = 4 * k + j;
+          const float4 g0 = __ldg(reinterpret_cast<const float4 *>(ln + ch * 8)), g1 = __ldg(reinterpret_cast<const float4 *>(ln + ch * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ln + CIN + ch * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(ln + CIN + ch * 8 + 4));
+          const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[k * 8 + i], rstd, nmr), gam[i], bet[i]);
+          *reinterpret_cast<uint4 *>(out + (((size_t)t * KC + ch) * hw + (size_t)gy * W + gx) * 8) = pack8(o);
+        }
+      }
+    }
+    return;
+  }
   for (int i = tid; i < TS * TS * CH; i += 256) {
     const int ch = i % CH, p = i / CH;
     const int gy = y0 + p / TS, gx = x0 + (p % TS);
@@ -519,6 +578,32 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   }
   count_launch();
   return check_launch("shift_conv1");
+}
+
+extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,
+                                  void *a1, void *stream) {
+  using namespace gsn;
+  GSN_REQUIRE(x && wc1 && ln && a1, "shift_conv1_ln: null pointer");
+  GSN_REQUIRE(T > 0 && H > 0 && W > 0, "shift_conv1_ln: empty shape");
+  GSN_REQUIRE(mode == GSN_MODE_CAB2_FWD || mode == GSN_MODE_CAB2_REV, "shift_conv1_ln: mode=%d is not a shift mode", mode);
+  if (C != 64) { set_error("shift_conv1_ln: C=%d unsupported (64)", C); return GSN_E_UNSUPPORTED; }
+  constexpr int smem = (34 * 34 + 16 * 16) * 32 * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(shift_conv1_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (!encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34)) {
+    set_error("shift_conv1_ln: cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", W, H, T);
+    return GSN_E_CUDA;
+  }
+  dim3 grid((W + 15) / 16, (H + 15) / 16, T);
+  shift_conv1_kernel<64, true, true><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half *>(x), T, H, W, mode, circular, reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(a1), tm, ln);
+  count_launch();
+  return check_launch("shift_conv1_ln");
 }
 
 extern "C" int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circular, const void *wc1, const float *ln,

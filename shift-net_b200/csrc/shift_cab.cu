@@ -407,19 +407,24 @@ __global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__
 // ------------------------------------------------------------------------------------------------
 // pass B: out = shortcut + Weff_t z (+ beff)
 // ------------------------------------------------------------------------------------------------
+// Persistent CTAs (grid = resident CTAs), 128-pixel tiles, two shared-memory stages: the cp.async loads of the next tile
+// (z, rolled shortcut, this frame's folded weight) are in flight while the current tile runs its MMAs and stores.
 template <int C>
-__global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
+__global__ void __launch_bounds__(256, 2) cab_pass_b_kernel(const GsnCabPassB d) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, NT = C / 8;
+  constexpr int STAGE = 2 * KC * PZ + KC * C * 16;
   extern __shared__ __align__(128) unsigned char smem_b[];
-  unsigned char *sz = smem_b, *ss = smem_b + KC * PZ, *sw = smem_b + 2 * KC * PZ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = blockIdx.y;
-  const long long hw = (long long)d.H * d.W, p0 = (long long)blockIdx.x * MP;
+  const long long hw = (long long)d.H * d.W;
+  const int tiles_f = (int)((hw + MP - 1) / MP), total = tiles_f * d.T;
   const size_t frame = (size_t)hw * C;
-  const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
   const __half *xg = reinterpret_cast<const __half *>(d.x);
-  const __half *zg = reinterpret_cast<const __half *>(d.z) + (size_t)t * frame;
-  {
+  auto load_tile = [&](int tile, int stage) {
+    unsigned char *sz = smem_b + stage * STAGE, *ss = sz + KC * PZ, *sw = sz + 2 * KC * PZ;
+    const int t = tile / tiles_f;
+    const long long p0 = (long long)(tile - t * tiles_f) * MP;
+    const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
+    const __half *zg = reinterpret_cast<const __half *>(d.z) + (size_t)t * frame;
     const unsigned char *wg = reinterpret_cast<const unsigned char *>(d.weff) + (size_t)t * C * C * 2;
     for (int i = tid; i < KC * C; i += 256) cp_async16(sw + i * 16, wg + i * 16, true);
     for (int i = tid; i < MP * KC; i += 256) {
@@ -433,9 +438,20 @@ __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
       cp_async16(ss + ch * PZ + p * 16, sp, valid);
     }
     cp_async_commit();
+  };
+  int tile = blockIdx.x, stage = 0;
+  if (tile < total) load_tile(tile, 0);
+  for (; tile < total; tile += gridDim.x, stage ^= 1) {
+  unsigned char *sz = smem_b + stage * STAGE, *ss = sz + KC * PZ, *sw = sz + 2 * KC * PZ;
+  const int t = tile / tiles_f;
+  const long long p0 = (long long)(tile - t * tiles_f) * MP;
+  if (tile + (int)gridDim.x < total) {     // the other stage was released by the barrier that ended the previous iteration
+    load_tile(tile + (int)gridDim.x, stage ^ 1);
+    cp_async_wait<1>();
+  } else {
     cp_async_wait<0>();
-    __syncthreads();
   }
+  __syncthreads();
   const int g = lane >> 2, tig = lane & 3;
   float acc[NT][4];
 #pragma unroll
@@ -457,6 +473,8 @@ __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
     }
   }
   const float *be = d.beff + (size_t)t * C;
+  const bool ln_next = C == 64 && d.a1_next != nullptr;
+  float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};   // LayerNorm statistics of the two pixel rows this thread holds a quarter of
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     const float b0 = __ldg(be + n * 8 + tig * 2), b1 = __ldg(be + n * 8 + tig * 2 + 1);
@@ -464,7 +482,41 @@ __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
     for (int hrow = 0; hrow < 2; ++hrow) {
       uint32_t *sp = reinterpret_cast<uint32_t *>(ss + n * PZ + (warp * 16 + g + hrow * 8) * 16 + tig * 4);
       const float2 s = unpack_half2(*sp);
-      *sp = pack_half2(s.x + acc[n][hrow * 2] + b0, s.y + acc[n][hrow * 2 + 1] + b1);
+      const uint32_t o = pack_half2(s.x + acc[n][hrow * 2] + b0, s.y + acc[n][hrow * 2 + 1] + b1);
+      *sp = o;
+      if (ln_next) {   // keep the fp16-rounded values: the LayerNorm sees what the next kernel would read from HBM
+        const float2 r = unpack_half2(o);
+        acc[n][hrow * 2] = r.x; acc[n][hrow * 2 + 1] = r.y;
+        s1[hrow] += r.x + r.y;
+        s2[hrow] = fmaf(r.x, r.x, fmaf(r.y, r.y, s2[hrow]));
+      }
+    }
+  }
+  if (ln_next) {
+    // a quad (tig = 0..3) holds the 64 channels of a pixel: two shuffles finish the statistics; the normalised values go to
+    // the z planes (this warp's 16 rows of sz were only read by this warp's ldmatrix above: no CTA barrier needed)
+    float rstd[2], nmr[2];
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      s1[hrow] += __shfl_xor_sync(0xffffffffu, s1[hrow], 1);
+      s2[hrow] += __shfl_xor_sync(0xffffffffu, s2[hrow], 1);
+      s1[hrow] += __shfl_xor_sync(0xffffffffu, s1[hrow], 2);
+      s2[hrow] += __shfl_xor_sync(0xffffffffu, s2[hrow], 2);
+      const float mu = s1[hrow] * (1.f / C);
+      rstd[hrow] = rsqrtf(fmaxf(s2[hrow] * (1.f / C) - mu * mu, 0.f) + 1e-6f);
+      nmr[hrow] = -mu * rstd[hrow];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float2 gm = __ldg(reinterpret_cast<const float2 *>(d.ln_next + n * 8 + tig * 2));
+      const float2 bt = __ldg(reinterpret_cast<const float2 *>(d.ln_next + C + n * 8 + tig * 2));
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        uint32_t *sp = reinterpret_cast<uint32_t *>(sz + n * PZ + (warp * 16 + g + hrow * 8) * 16 + tig * 4);
+        *sp = pack_half2(fmaf(fmaf(acc[n][hrow * 2], rstd[hrow], nmr[hrow]), gm.x, bt.x),
+                         fmaf(fmaf(acc[n][hrow * 2 + 1], rstd[hrow], nmr[hrow]), gm.y, bt.y));
+      }
     }
   }
   __syncthreads();
@@ -474,6 +526,19 @@ __global__ void __launch_bounds__(256) cab_pass_b_kernel(const GsnCabPassB d) {
     if (p0 + p < hw)
       *reinterpret_cast<uint4 *>(og + (size_t)(p0 + p) * C + ch * 8) = *reinterpret_cast<const uint4 *>(ss + ch * PZ + p * 16);
   }
+  // Optional (C = 64): the LayerNorm of the NEXT block (CAB1.norm, gshift_deblur2.py:209) of the fp16 `out` values, staged in
+  // the (dead) z planes above and written here in the k-chunk planar layout [T][C/8][H*W][8] that the pre-normalised pass A
+  // lands by TMA (GsnCabPassA.a1_pre); lanes run along the pixels of one plane -> 512-byte contiguous stores.
+  if (C == 64 && d.a1_next) {
+    __half *ag = reinterpret_cast<__half *>(d.a1_next) + (size_t)t * KC * hw * 8;
+    for (int i = tid; i < MP * KC; i += 256) {
+      const int ch = i / MP, p = i % MP;
+      if (p0 + p < hw)
+        *reinterpret_cast<uint4 *>(ag + ((size_t)ch * hw + (p0 + p)) * 8) = *reinterpret_cast<const uint4 *>(sz + ch * PZ + p * 16);
+    }
+  }
+  __syncthreads();   // all reads of this stage are done: the next iteration prefetches into it
+  }   // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,18 +780,27 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   GSN_REQUIRE(dp != nullptr, "cab_pass_b: null descriptor");
   const GsnCabPassB &d = *dp;
   GSN_REQUIRE(d.x && d.z && d.weff && d.beff && d.out, "cab_pass_b: null pointer");
+  GSN_REQUIRE(!d.a1_next || (d.ln_next && d.C == 64), "cab_pass_b: a1_next needs ln_next and C=64");
   GSN_REQUIRE(d.T > 0 && d.H > 0 && d.W > 0, "cab_pass_b: empty shape");
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_b: mode=%d", d.mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long hw = (long long)d.H * d.W;
-  dim3 grid((unsigned)((hw + 127) / 128), d.T);
+  const long long total_tiles = (hw + 127) / 128 * d.T;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const unsigned grid = (unsigned)(total_tiles < 2LL * num_sms ? total_tiles : 2LL * num_sms);   // persistent, 2 CTAs per SM
   if (d.C == 64) {
-    constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
+    constexpr int smem = 2 * (2 * 8 * 129 * 16 + 8 * 64 * 16);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     cab_pass_b_kernel<64><<<grid, 256, smem, st>>>(d);
   } else if (d.C == 80) {
-    constexpr int smem = 2 * 10 * 129 * 16 + 10 * 80 * 16;
+    constexpr int smem = 2 * (2 * 10 * 129 * 16 + 10 * 80 * 16);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     cab_pass_b_kernel<80><<<grid, 256, smem, st>>>(d);

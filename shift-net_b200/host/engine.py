@@ -34,6 +34,10 @@ class Engine:
         # LayerNorm of CAB1/CAB2 as its own HBM-bound kernel writing the k-chunk planar operand that pass A lands by TMA
         # directly in the tensor-core layout (csrc/cab_pass_a_pre.cu); GSN_PASS_A_PRE=0 keeps the LayerNorm inside pass A
         self.pass_a_pre = os.environ.get("GSN_PASS_A_PRE", "1") == "1" and self.shift_split
+        # ... and that LayerNorm fused into its producers: CAB2's into the shift gather + conv1 kernel (gsn_shift_conv1_ln), CAB1's
+        # into the epilogue of the preceding pass B (GsnCabPassB.a1_next); GSN_LN_FUSE=0 runs it as gsn_ln_planar
+        self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
+        self._a1_next = None
         # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
         self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"
         # optional per-kernel timing (bench.py's roofline leg): list of (name, pixels, start_event, end_event)
@@ -211,7 +215,13 @@ class Engine:
         return self.seq_cabs(p + ".decoder_level1", y, c1)
 
     # ------------------------------------------------------------------ fused shift + NAF block
-    def _fold_and_pass_b(self, p, x, z, partial, ntiles, fw, mode):
+    def _ln_params(self, p):
+        ck = ("ln", p)
+        if ck not in self.cache:
+            self.cache[ck] = torch.cat((self.sd[p + ".norm.weight"].float(), self.sd[p + ".norm.bias"].float())).contiguous()
+        return self.cache[ck]
+
+    def _fold_and_pass_b(self, p, x, z, partial, ntiles, fw, mode, next_p=None):
         T, H, W, Cc = x.shape
         weff = self._new(T, Cc * Cc)
         beff = self._new(T, Cc, dtype=torch.float32)
@@ -223,6 +233,10 @@ class Engine:
         b = L.CabPassB()
         b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
+        self._a1_next = None
+        if next_p is not None:      # the LayerNorm of the block that consumes `out` rides on this kernel's epilogue
+            self._a1_next = self._new(T, Cc // 8, H, W, 8)
+            b.ln_next, b.a1_next = self._ln_params(next_p).data_ptr(), self._a1_next.data_ptr()
         with self._timed(f"cab_pass_b[{H}x{W}]" if self.timeline_detail else "cab_pass_b", T * H * W):
             L.check(self.lib.gsn_cab_pass_b(C.byref(b), self._stream()), "cab_pass_b " + p)
         return out
@@ -290,8 +304,11 @@ class Engine:
         L.check(self.lib.gsn_roll_copy(x.data_ptr(), y.data_ptr(), T, H, W, c, cp, 1 if reverse else 0, self._stream()), "roll_copy")
         return self.cab(p, y, c)
 
-    def gated_cab(self, p, x, mode, debug_stage=0):
-        """One CAB2 (mode fwd/rev: shift folded into the load) or CAB1 step: pass A -> fold -> pass B."""
+    def gated_cab(self, p, x, mode, debug_stage=0, a1_pre=None, next_p=None):
+        """One CAB2 (mode fwd/rev: shift folded into the load) or CAB1 step: pass A -> fold -> pass B.
+        a1_pre: the block's LayerNorm output if a producer already made it (pass B epilogue of the previous block);
+        next_p: name of the CAB1 that consumes the result -- its LayerNorm is then emitted by this block's pass B
+        (left in ``self._a1_next``)."""
         T, H, W, Cc = x.shape
         if Cc != 64:
             return self.gated_cab_generic(p, x, mode)
@@ -307,7 +324,16 @@ class Engine:
         a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), partial.data_ptr()
         a.mid_ca = 1 if self.spec.denoise else 0
-        if shift and self.shift_split:
+        fuse_shift_ln = shift and self.pass_a_pre and self.ln_fuse
+        if fuse_shift_ln:
+            ckw = ("wc1", p)
+            if ckw not in self.cache:
+                self.cache[ckw] = self.sd[p + ".conv1.weight"].view(Cc // 2, 9).t().contiguous().half()
+            a1_pre = self._new(T, 12, H, W, 8)
+            with self._timed("shift_conv1_ln", T * H * W):
+                L.check(self.lib.gsn_shift_conv1_ln(x.data_ptr(), T, H, W, Cc, mode, a.circular, self.cache[ckw].data_ptr(),
+                                                    self._ln_params(p).data_ptr(), a1_pre.data_ptr(), self._stream()), "shift_conv1_ln " + p)
+        elif shift and self.shift_split:
             ckw = ("wc1", p)
             if ckw not in self.cache:
                 self.cache[ckw] = self.sd[p + ".conv1.weight"].view(Cc // 2, 9).t().contiguous().half()
@@ -317,14 +343,12 @@ class Engine:
                                                  hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
             a.hw_pre = hw_pre.data_ptr()
         if self.pass_a_pre:
-            ckl = ("ln", p)
-            if ckl not in self.cache:
-                self.cache[ckl] = torch.cat((self.sd[p + ".norm.weight"].float(), self.sd[p + ".norm.bias"].float())).contiguous()
-            a1 = self._new(T, 12 if shift else 8, H, W, 8)
-            with self._timed("ln_planar", T * H * W):
-                L.check(self.lib.gsn_ln_planar(x.data_ptr(), a.hw_pre, T, H, W, Cc, mode, a.circular, self.cache[ckl].data_ptr(),
-                                               a1.data_ptr(), self._stream()), "ln_planar " + p)
-            a.a1_pre = a1.data_ptr()
+            if a1_pre is None:
+                a1_pre = self._new(T, 12 if shift else 8, H, W, 8)
+                with self._timed("ln_planar", T * H * W):
+                    L.check(self.lib.gsn_ln_planar(x.data_ptr(), a.hw_pre, T, H, W, Cc, mode, a.circular, self._ln_params(p).data_ptr(),
+                                                   a1_pre.data_ptr(), self._stream()), "ln_planar " + p)
+            a.a1_pre = a1_pre.data_ptr()
         dbg = None
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
@@ -344,7 +368,7 @@ class Engine:
             with self._timed("cab_pass_a2", T * H * W):
                 L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2eff.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 1,
                                                  self._stream()), "cab_pass_a2")
-        out = self._fold_and_pass_b(p, x, z, partial, ntiles, fw, mode)
+        out = self._fold_and_pass_b(p, x, z, partial, ntiles, fw, mode, next_p=next_p)
         if debug_stage:
             return out, z, dbg
         return out
@@ -353,8 +377,9 @@ class Engine:
         """Encoder_shift_block.forward (gshift_deblur2.py:521-530): alternating fwd/rev (shift, CAB2, CAB1) pairs."""
         for i in range(self.spec.pairs):
             q = f"{p}.{_PAIRS[i]}"
-            x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if (i & 1) else L.MODE_CAB2_FWD)
-            x = self.gated_cab(q + ".1", x, L.MODE_CAB1)
+            fuse = self.pass_a_pre and self.ln_fuse and x.shape[-1] == 64
+            x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if (i & 1) else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
+            x = self.gated_cab(q + ".1", x, L.MODE_CAB1, a1_pre=self._a1_next if fuse else None)
         return x
 
     # ------------------------------------------------------------------ stage 1 (Encoder2, Ours-s topology)

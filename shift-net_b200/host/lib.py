@@ -14,7 +14,7 @@ EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
-    "gsn_shift_conv1", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
+    "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
     "gsn_cab_dense_tiles", "gsn_cab_dense",
 ]
 
@@ -54,6 +54,7 @@ class CabPassB(C.Structure):
     _fields_ = [
         ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("mode", C.c_int), ("circular", C.c_int),
         ("x", C.c_void_p), ("z", C.c_void_p), ("weff", C.c_void_p), ("beff", C.c_void_p), ("out", C.c_void_p),
+        ("ln_next", C.c_void_p), ("a1_next", C.c_void_p),
     ]
 
 
@@ -90,6 +91,7 @@ def load():
     lib.gsn_cab_tiles_linear.argtypes = [ll]
     lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
     lib.gsn_shift_conv1.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp]
+    lib.gsn_shift_conv1_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp]
     lib.gsn_ln_planar.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp]
     lib.gsn_shift_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, i, vp, vp]
     lib.gsn_ln_pw.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp, vp, vp]

@@ -285,6 +285,17 @@ def test_pass_a_pre_normalised_vs_in_kernel_layernorm(arch):
         else:
             ref = O.cab2(sd, p, O.channel_shift(x, which == "cab2_rev", spec.circular), spec.c1, spec.denoise)
         check(a, ref, 3e-3, f"{arch} {which}: pre-normalised vs oracle")
+    # whole shift block: LayerNorm fused into its producers (shift_conv1_ln, pass-B epilogue) vs the stand-alone ln_planar
+    # kernel vs the in-kernel LayerNorm
+    eng_planar = gio.pkg("host.engine").Engine(spec, {}, DEV)
+    eng_planar.sd = eng.sd
+    eng_planar.ln_fuse = False
+    xb = to_nhwc(x)
+    a = from_nhwc(eng.shift_block("stage1.decoder_level1", xb), spec.c1)
+    b = from_nhwc(eng_planar.shift_block("stage1.decoder_level1", xb), spec.c1)
+    c = from_nhwc(eng_ref.shift_block("stage1.decoder_level1", xb), spec.c1)
+    check(a, b, 5e-4, f"{arch} shift block: fused LayerNorm producers vs ln_planar")
+    check(a, c, 1e-3, f"{arch} shift block: pre-normalised vs in-kernel LayerNorm")
 
 
 def test_shift_block(aenv):
