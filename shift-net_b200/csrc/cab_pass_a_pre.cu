@@ -132,12 +132,6 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  // Equal tiles keep the 148 persistent CTAs in lockstep, so all their A1 loads (60-90 KB each) would hit HBM in the same
-  // instant and arrive late; a one-off start skew of a quarter tile per CTA (mod 4) spreads them for the whole launch.
-  if (d.debug_stage != 8 && (blockIdx.x & 3)) {
-    const long long until = clock64() + (long long)(blockIdx.x & 3) * 4096;
-    while (clock64() < until) { }
-  }
   if (tid == 0) issue_a1(t, x0, y0);
   for (int i = tid; i < K::W1_BYTES / 16; i += kPreThreads) cp_async16(smem + K::S_W1 + i * 16, wb + K::OFF_W1 + i * 16, true);
   for (int i = tid; i < K::WT2_BYTES / 16; i += kPreThreads) cp_async16(smem + K::S_WT2 + i * 16, wb + K::OFF_DA + i * 16, true);

@@ -407,24 +407,19 @@ __global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__
 // ------------------------------------------------------------------------------------------------
 // pass B: out = shortcut + Weff_t z (+ beff)
 // ------------------------------------------------------------------------------------------------
-// Persistent CTAs (grid = resident CTAs), 128-pixel tiles, two shared-memory stages: the cp.async loads of the next tile
-// (z, rolled shortcut, this frame's folded weight) are in flight while the current tile runs its MMAs and stores.
 template <int C>
-__global__ void __launch_bounds__(256, 2) cab_pass_b_kernel(const GsnCabPassB d) {
+__global__ void __launch_bounds__(256, (C <= 64 ? 4 : 1)) cab_pass_b_kernel(const GsnCabPassB d) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, NT = C / 8;
-  constexpr int STAGE = 2 * KC * PZ + KC * C * 16;
   extern __shared__ __align__(128) unsigned char smem_b[];
+  unsigned char *sz = smem_b, *ss = smem_b + KC * PZ, *sw = smem_b + 2 * KC * PZ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long hw = (long long)d.H * d.W;
-  const int tiles_f = (int)((hw + MP - 1) / MP), total = tiles_f * d.T;
+  const int t = blockIdx.y;
+  const long long hw = (long long)d.H * d.W, p0 = (long long)blockIdx.x * MP;
   const size_t frame = (size_t)hw * C;
+  const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
   const __half *xg = reinterpret_cast<const __half *>(d.x);
-  auto load_tile = [&](int tile, int stage) {
-    unsigned char *sz = smem_b + stage * STAGE, *ss = sz + KC * PZ, *sw = sz + 2 * KC * PZ;
-    const int t = tile / tiles_f;
-    const long long p0 = (long long)(tile - t * tiles_f) * MP;
-    const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
-    const __half *zg = reinterpret_cast<const __half *>(d.z) + (size_t)t * frame;
+  const __half *zg = reinterpret_cast<const __half *>(d.z) + (size_t)t * frame;
+  {
     const unsigned char *wg = reinterpret_cast<const unsigned char *>(d.weff) + (size_t)t * C * C * 2;
     for (int i = tid; i < KC * C; i += 256) cp_async16(sw + i * 16, wg + i * 16, true);
     for (int i = tid; i < MP * KC; i += 256) {
@@ -438,20 +433,9 @@ __global__ void __launch_bounds__(256, 2) cab_pass_b_kernel(const GsnCabPassB d)
       cp_async16(ss + ch * PZ + p * 16, sp, valid);
     }
     cp_async_commit();
-  };
-  int tile = blockIdx.x, stage = 0;
-  if (tile < total) load_tile(tile, 0);
-  for (; tile < total; tile += gridDim.x, stage ^= 1) {
-  unsigned char *sz = smem_b + stage * STAGE, *ss = sz + KC * PZ, *sw = sz + 2 * KC * PZ;
-  const int t = tile / tiles_f;
-  const long long p0 = (long long)(tile - t * tiles_f) * MP;
-  if (tile + (int)gridDim.x < total) {     // the other stage was released by the barrier that ended the previous iteration
-    load_tile(tile + (int)gridDim.x, stage ^ 1);
-    cp_async_wait<1>();
-  } else {
     cp_async_wait<0>();
+    __syncthreads();
   }
-  __syncthreads();
   const int g = lane >> 2, tig = lane & 3;
   float acc[NT][4];
 #pragma unroll
@@ -537,8 +521,6 @@ __global__ void __launch_bounds__(256, 2) cab_pass_b_kernel(const GsnCabPassB d)
         *reinterpret_cast<uint4 *>(ag + ((size_t)ch * hw + (p0 + p)) * 8) = *reinterpret_cast<const uint4 *>(sz + ch * PZ + p * 16);
     }
   }
-  __syncthreads();   // all reads of this stage are done: the next iteration prefetches into it
-  }   // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -785,22 +767,14 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_b: mode=%d", d.mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long hw = (long long)d.H * d.W;
-  const long long total_tiles = (hw + 127) / 128 * d.T;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
-  const unsigned grid = (unsigned)(total_tiles < 2LL * num_sms ? total_tiles : 2LL * num_sms);   // persistent, 2 CTAs per SM
+  dim3 grid((unsigned)((hw + 127) / 128), d.T);
   if (d.C == 64) {
-    constexpr int smem = 2 * (2 * 8 * 129 * 16 + 8 * 64 * 16);
+    constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     cab_pass_b_kernel<64><<<grid, 256, smem, st>>>(d);
   } else if (d.C == 80) {
-    constexpr int smem = 2 * (2 * 10 * 129 * 16 + 10 * 80 * 16);
+    constexpr int smem = 2 * 10 * 129 * 16 + 10 * 80 * 16;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     cab_pass_b_kernel<80><<<grid, 256, smem, st>>>(d);
