@@ -670,6 +670,7 @@ constexpr int kTileH_Cab1 = 16, kTileH_Cab2 = 8;
 
 int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st);  // cab_pass_a_tc.cu
 int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
+int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b_tc.cu
 
 // GSN_PASS_A_LEGACY=1 selects the mma.sync cross-check implementation of pass A (tests / bisecting only).
 static bool use_legacy_pass_a() {
@@ -767,6 +768,9 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_b: mode=%d", d.mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long hw = (long long)d.H * d.W;
+  // C = 64: the TMA / tcgen05 streaming kernel (cab_pass_b_tc.cu); GSN_PASS_B_TC=0 keeps the mma.sync kernel below
+  static const bool want_tc = [] { const char *e = getenv("GSN_PASS_B_TC"); return !(e && e[0] == '0'); }();
+  if (d.C == 64 && want_tc) return cab_pass_b_tc_dispatch(d, st);
   dim3 grid((unsigned)((hw + 127) / 128), d.T);
   if (d.C == 64) {
     constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
