@@ -163,7 +163,13 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
   const int nt = tile + (int)gridDim.x;
   const bool has_next = nt < total_tiles;
   int nt_t = 0, nt_x0 = 0, nt_y0 = 0;
-  if (has_next) decode(nt, nt_t, nt_x0, nt_y0);
+  if (has_next) {   // advance (frame, tile row, tile column) by gridDim.x tiles without integer divisions
+    int tx = x0 / K::TW + (int)gridDim.x, ty = y0 / K::TH;   // TW, TH are powers of two
+    nt_t = t;
+    while (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    while (ty >= tiles_y) { ty -= tiles_y; ++nt_t; }
+    nt_x0 = tx * K::TW; nt_y0 = ty * K::TH;
+  }
 
   // ---- P2: GEMM1 of this tile was issued during the previous tile (or in P0) ------------------------------------------
   mbar_wait(bar_g1, g1_parity);

@@ -361,15 +361,16 @@ __global__ void __launch_bounds__(kThreads, 1) cab_pass_a_kernel(const GsnCabPas
 // ------------------------------------------------------------------------------------------------
 // fold: CALayer2 MLP + beta folded into the per-frame last 1x1
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
+__global__ void __launch_bounds__(1024) cab_fold_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
                                                        const float *__restrict__ w_du0, const float *__restrict__ w_du2,
                                                        int cr, const float *__restrict__ w3, const float *__restrict__ beta,
                                                        const float *__restrict__ bias3, int C, __half *__restrict__ weff,
                                                        float *__restrict__ beff) {
-  __shared__ float mean[128], hid[128], sc[128], part[256];
+  __shared__ float mean[128], hid[128], sc[128], part[1024];
   const int t = blockIdx.x, tid = threadIdx.x;
-  {  // deterministic two-level reduction of the per-tile channel sums
-    const int nparts = 256 / C, ch = tid % C, pi = tid / C;
+  {  // deterministic two-level reduction of the per-tile channel sums (1024 threads: the ~900 dependent adds per channel of a
+     // 720p level-1 frame become ~60 per thread -- this latency-bound kernel runs 96 times per forward)
+    const int nparts = 1024 / C, ch = tid % C, pi = tid / C;
     float a = 0.f;
     if (pi < nparts) {
       const float *p = partial + (size_t)t * ntiles * C + ch;
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(256) cab_fold_kernel(const float *__restrict__
   }
   __syncthreads();
   __half *wt = weff + (size_t)t * C * C;
-  for (int i = tid; i < C * C; i += 256) {
+  for (int i = tid; i < C * C; i += 1024) {
     const int co = i / C, ci = i - co * C;
     wt[((ci >> 3) * C + co) * 8 + (ci & 7)] = __float2half_rn(beta[co] * w3[co * C + ci] * sc[ci]);
   }
@@ -752,7 +753,7 @@ extern "C" int gsn_cab_fold(const float *partial, int ntiles, float inv_hw, cons
   using namespace gsn;
   GSN_REQUIRE(partial && w_du0 && w_du2 && w3 && beta && weff && beff, "cab_fold: null pointer");
   GSN_REQUIRE(C > 0 && C <= 128 && C % 8 == 0 && cr > 0 && cr <= 128 && ntiles > 0 && T > 0, "cab_fold: bad sizes C=%d cr=%d", C, cr);
-  cab_fold_kernel<<<T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, ntiles, inv_hw, w_du0, w_du2, cr, w3, beta,
+  cab_fold_kernel<<<T, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, ntiles, inv_hw, w_du0, w_du2, cr, w3, beta,
                                                                           bias3, C, reinterpret_cast<__half *>(weff), beff);
   count_launch();
   return check_launch("cab_fold");
