@@ -214,45 +214,53 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
   {
     constexpr int NSTRIP = 3, SROWS = (K::R2H + NSTRIP - 1) / NSTRIP;  // 7,7,6 output rows
     const unsigned char *wda = smem + K::S_WT2;
+    // Branch-free strips: every strip runs SROWS output rows (the 7th row of the last strip reads one region row past the
+    // plane -- still inside the allocation -- and its store is predicated off); the zero padding outside the image is a
+    // bit mask on the packed result.  No control flow inside the row loop, so the loads of the next rows are scheduled under
+    // the HFMA2s of the current one.
+    static_assert(K::S_G1 + (K::NC - 1) * K::P1 + ((NSTRIP * SROWS + 2) * K::R1W + 2) * 16 <= K::SMEM, "over-read stays inside smem");
     for (int item = tid; item < K::KC2 * K::R2W * NSTRIP; item += kPreThreads) {
       const int x = item % K::R2W, rest = item / K::R2W;
       const int p = rest % K::KC2, strip = rest / K::KC2;
-      const int r0 = strip * SROWS, r1 = min(r0 + SROWS, K::R2H);
+      const int r0 = strip * SROWS;
+      const int gx = x0 - 2 + x;
+      const bool xok = gx >= 0 && gx < d.W;
       H8 res[SROWS];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int chunk = half * K::KC2 + p;
-        const unsigned char *pl = smem + K::S_G1 + chunk * K::P1;
+        const unsigned char *pl = smem + K::S_G1 + chunk * K::P1 + (r0 * K::R1W + x) * 16;
         H8 w[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) w[i] = lds_h8(wda + (i * 2 * C + chunk * 8) * 2);
         H8 acc0, acc1;
 #pragma unroll
         for (int i = 0; i < SROWS + 2; ++i) {           // input region row r0 + i feeds output rows (r0+i-2 .. r0+i)
-          const int row = r0 + i;
-          if (row < r1 + 2) {
-            const unsigned char *rp = pl + (row * K::R1W + x) * 16;
-            const H8 v0 = lds_h8(rp), v1 = lds_h8(rp + 16), v2 = lds_h8(rp + 32);
-            if (i >= 2) {                               // output row r0+i-2 completes with kernel row 2
-              h8_fma(acc0, v0, w[6]); h8_fma(acc0, v1, w[7]); h8_fma(acc0, v2, w[8]);
-              if (half == 0) res[i - 2] = acc0;
-              else {
-                const int orow = row - 2;
-                const int gy = y0 - 2 + orow, gx = x0 - 2 + x;
-                H8 o;
-                if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) h8_mul(o, res[i - 2], acc0);
-                else {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) o.h[q] = __float2half2_rn(0.f);
-                }
-                sts_h8(smem + K::S_GT + p * K::P2 + (orow * K::R2W + x) * 16, o);
-              }
+          const unsigned char *rp = pl + i * K::R1W * 16;
+          const H8 v0 = lds_h8(rp), v1 = lds_h8(rp + 16), v2 = lds_h8(rp + 32);
+          if (i >= 2) {                                 // output row r0+i-2 completes with kernel row 2
+            h8_fma(acc0, v0, w[6]); h8_fma(acc0, v1, w[7]); h8_fma(acc0, v2, w[8]);
+            if (half == 0) res[i - 2] = acc0;
+            else {
+              const int orow = r0 + i - 2;
+              const int gy = y0 - 2 + orow;
+              const uint32_t mask = (xok && gy >= 0 && gy < d.H) ? 0xffffffffu : 0u;
+              H8 o;
+              h8_mul(o, res[i - 2], acc0);
+              uint4 ov;
+              ov.x = *reinterpret_cast<const uint32_t *>(&o.h[0]) & mask;
+              ov.y = *reinterpret_cast<const uint32_t *>(&o.h[1]) & mask;
+              ov.z = *reinterpret_cast<const uint32_t *>(&o.h[2]) & mask;
+              ov.w = *reinterpret_cast<const uint32_t *>(&o.h[3]) & mask;
+              if (orow < K::R2H) *reinterpret_cast<uint4 *>(smem + K::S_GT + p * K::P2 + (orow * K::R2W + x) * 16) = ov;
             }
-            if (i >= 1) {                               // output row r0+i-1: kernel row 1 (centre row)
-              acc0 = acc1;
-              h8_fma(acc0, v0, w[3]); h8_fma(acc0, v1, w[4]); h8_fma(acc0, v2, w[5]);   // w[4] carries the "+ x" of RepConv2
-            }
-            h8_mul(acc1, v0, w[0]);                     // output row r0+i: kernel row 0 starts a new accumulator
+          }
+          if (i >= 1 && i <= SROWS) {                   // output row r0+i-1: kernel row 1 (centre row)
+            acc0 = acc1;
+            h8_fma(acc0, v0, w[3]); h8_fma(acc0, v1, w[4]); h8_fma(acc0, v2, w[5]);   // w[4] carries the "+ x" of RepConv2
+          }
+          if (i < SROWS) {                              // output row r0+i: kernel row 0 starts a new accumulator
+            h8_mul(acc1, v0, w[0]);
             h8_fma(acc1, v1, w[1]); h8_fma(acc1, v2, w[2]);
           }
         }
