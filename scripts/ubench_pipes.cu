@@ -141,6 +141,59 @@ __global__ void k_ldm_hmma(float *out, long long *cyc, unsigned seed) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// MUFU: tanh.approx.f32 (one element per op) vs tanh.approx.f16x2 (two) -- the sigmoid gate of pass A is MUFU-bound
+template <int ILP, bool PACKED>
+__global__ void k_tanh(unsigned *out, long long *cyc, unsigned seed) {
+  unsigned a[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) a[i] = 0x34003400u + threadIdx.x + i + seed;
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      if (PACKED) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(a[i]));
+      else asm volatile("tanh.approx.f32 %0, %0;" : "+f"(*reinterpret_cast<float *>(&a[i])));
+    }
+  }
+  long long t1 = clock64();
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s ^= a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// do HFMA2 and FFMA share one pipe?  NH HFMA2 + NF FFMA per iteration, independent chains
+template <int NH, int NF>
+__global__ void k_hf_mix(unsigned *out, long long *cyc, unsigned seed) {
+  unsigned h[NH > 0 ? NH : 1], w0 = seed | 0x3c003c00u, w1 = seed ^ 0x38003800u;
+  float f[NF > 0 ? NF : 1], g0 = 1.0001f, g1 = 0.5f;
+#pragma unroll
+  for (int i = 0; i < NH; ++i) h[i] = threadIdx.x + i;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) f[i] = threadIdx.x + i;
+  __syncthreads();
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < (NH > NF ? NH : NF); ++i) {
+      if (i < NH) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(h[i]) : "r"(w0), "r"(w1));
+      if (i < NF) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(g0), "f"(g1));
+    }
+  }
+  long long t1 = clock64();
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < NH; ++i) s ^= h[i];
+#pragma unroll
+  for (int i = 0; i < NF; ++i) s ^= __float_as_uint(f[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 template <typename F>
 static void run(const char *name, F launch, int threads, double winstr_per_thread_iter) {
   unsigned *out;
@@ -178,6 +231,10 @@ int main() {
     run("HFMA2 ILP16", [&](unsigned *o, long long *c) { k_hfma2<16><<<148, threads>>>(o, c, 1); }, threads, 16);
     run("FFMA ILP8", [&](unsigned *o, long long *c) { k_ffma<8><<<148, threads>>>((float *)o, c, 1.f); }, threads, 8);
     run("FFMA ILP16", [&](unsigned *o, long long *c) { k_ffma<16><<<148, threads>>>((float *)o, c, 1.f); }, threads, 16);
+    run("MUFU tanh.approx.f32 ILP8", [&](unsigned *o, long long *c) { k_tanh<8, false><<<148, threads>>>(o, c, 1); }, threads, 8);
+    run("MUFU tanh.approx.f16x2 ILP8", [&](unsigned *o, long long *c) { k_tanh<8, true><<<148, threads>>>(o, c, 1); }, threads, 8);
+    run("8 HFMA2 + 8 FFMA (co-issue?)", [&](unsigned *o, long long *c) { k_hf_mix<8, 8><<<148, threads>>>(o, c, 1); }, threads, 16);
+    run("8 HFMA2 + 4 FFMA", [&](unsigned *o, long long *c) { k_hf_mix<8, 4><<<148, threads>>>(o, c, 1); }, threads, 12);
     run("LDS.128 x4 only (xor)", [&](unsigned *o, long long *c) { k_mix<4, 0><<<148, threads, 65536>>>(o, c, 1); }, threads, 4);
     run("LDS.128 x3 + 36 HFMA2 (dw3x3 mix)", [&](unsigned *o, long long *c) { k_mix<3, 36><<<148, threads, 65536>>>(o, c, 1); }, threads, 39);
     run("LDS.128 x3 + 12 HFMA2", [&](unsigned *o, long long *c) { k_mix<3, 12><<<148, threads, 65536>>>(o, c, 1); }, threads, 15);

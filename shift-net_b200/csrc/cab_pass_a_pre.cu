@@ -185,11 +185,9 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
 
   // ---- P3: TMEM -> fp16 G1 planes (all 2C channels of the region) ----------------------------------------------
   {
-    const int quarter = warp & 3, sub = warp >> 2;   // a warp may only touch TMEM lanes [32*quarter, +32)
-    for (int u = sub; u < K::MT1 * (K::N / 32); u += kPreThreads / 128) {
-      const int m = u / (K::N / 32), cg = u % (K::N / 32);
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32, v);
+    const int quarter = warp & 3, cg = warp >> 2;   // a warp may only touch TMEM lanes [32*quarter, +32); one 32-column group per warp
+    static_assert(K::N / 32 == kPreThreads / 128 && K::MT1 % 2 == 0, "drain: one column group per warp, M tiles in pairs");
+    auto put = [&](const uint32_t (&v)[32], int m) {
       const int px = m * 128 + quarter * 32 + lane;
       if (px < K::M1) {
 #pragma unroll
@@ -202,8 +200,17 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
           *reinterpret_cast<uint4 *>(smem + K::S_G1 + (cg * 4 + c4) * K::P1 + px * 16) = o;
         }
       }
+    };
+#pragma unroll 1
+    for (int m = 0; m < K::MT1; m += 2) {     // two TMEM loads in flight before the first conversion
+      uint32_t v0[32], v1[32];
+      const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32;
+      tmem_ld32_nowait(ta, v0);
+      tmem_ld32_nowait(ta + K::N, v1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      put(v0, m);
+      put(v1, m + 1);
     }
-    if (!MIDCA && tid == kIssZ) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // previous z tile left smem
     tc_fence_before();
     __syncthreads();   // G1 complete; every thread is done with the previous tile's z staging / channel sums
     GSN_CLK();  // 2: TMEM -> G1 done
@@ -418,8 +425,9 @@ __global__ void __launch_bounds__(kPreThreads, 1) cab_pass_a_pre_kernel(const Gs
       const int m = sub / (C / 32), cg = sub % (C / 32);
       uint32_t a[32], b[32];
       const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + m * K::N + cg * 32;
-      tmem_ld32(base, a);
-      tmem_ld32(base + C, b);
+      tmem_ld32_nowait(base, a);
+      tmem_ld32_nowait(base + C, b);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
       // Both halves of GEMM2's output now sit in registers: TMEM columns [0, 2N) are free again.  Every warp signals that on
       // named barrier 1 without waiting; only the warp of thread kIssB waits for all 16 and then issues the rest of the next
       // tile's GEMM1 (M tiles 0,1), which runs under the sigmoid gate and the store.

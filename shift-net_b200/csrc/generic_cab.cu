@@ -16,6 +16,8 @@
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "shift_common.cuh"
 
@@ -437,44 +439,50 @@ __global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(con
     __syncthreads();
   }
   const bool interior = y0 >= 1 && y0 + TS + 1 <= H && x0 >= 1 && x0 + TS + 1 <= W;   // all destination taps in-image
-  for (int item = tid; item < HC * TS; item += 256) {
-    const int c = item % HC, oy = item / HC;
-    int dy, dx;
-    shift_offset<C>(c, dy, dx);
-    float w[9];
+  // INT = true: tile whose conv taps all land inside the image (the vast majority) -- no border predicates in the tap loop
+  auto conv_items = [&](auto int_tag) {
+    constexpr bool INT = decltype(int_tag)::value;
+    for (int item = tid; item < HC * TS; item += 256) {
+      const int c = item % HC, oy = item / HC;
+      int dy, dx;
+      shift_offset<C>(c, dy, dx);
+      float w[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = __half2float(__ldg(wc1 + i * HC + c));
-    const __half *rp = box + ((oy - 1 - dy + 9) * BW - dx + 9) * HC + c;   // (row oy+ty-1, col) -> rp[(ty*BW + col) * HC]
-    bool rowok[3];
+      for (int i = 0; i < 9; ++i) w[i] = __half2float(__ldg(wc1 + i * HC + c));
+      const __half *rp = box + ((oy - 1 - dy + 9) * BW - dx + 9) * HC + c;   // (row oy+ty-1, col) -> rp[(ty*BW + col) * HC]
+      bool rowok[3];
 #pragma unroll
-    for (int ty = 0; ty < 3; ++ty) { const int sy = y0 + oy + ty - 1; rowok[ty] = interior || (sy >= 0 && sy < H); }
-    float v[3][3];
-    auto load_col = [&](int col, float(&o)[3]) {
-      const int sx = x0 + col;
-      const bool cok = interior || (sx >= 0 && sx < W);
+      for (int ty = 0; ty < 3; ++ty) { const int sy = y0 + oy + ty - 1; rowok[ty] = INT || (sy >= 0 && sy < H); }
+      float v[3][3];
+      auto load_col = [&](int col, float(&o)[3]) {
+        const int sx = x0 + col;
+        const bool cok = INT || (sx >= 0 && sx < W);
 #pragma unroll
-      for (int ty = 0; ty < 3; ++ty) o[ty] = (cok && rowok[ty]) ? __half2float(rp[(ty * BW + col) * HC]) : 0.f;
-    };
-    {
-      float a[3], b[3];
-      load_col(-1, a);
-      load_col(0, b);
+        for (int ty = 0; ty < 3; ++ty) o[ty] = (INT || (cok && rowok[ty])) ? __half2float(rp[(ty * BW + col) * HC]) : 0.f;
+      };
+      {
+        float a[3], b[3];
+        load_col(-1, a);
+        load_col(0, b);
 #pragma unroll
-      for (int ty = 0; ty < 3; ++ty) { v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+        for (int ty = 0; ty < 3; ++ty) { v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+      }
+#pragma unroll
+      for (int ox = 0; ox < TS; ++ox) {
+        float nc[3];
+        load_col(ox + 1, nc);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) { v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty]; }
+        a0 = fmaf(v[0][0], w[0], fmaf(v[0][1], w[1], v[0][2] * w[2]));
+        a1 = fmaf(v[1][0], w[3], fmaf(v[1][1], w[4], v[1][2] * w[5]));
+        a2 = fmaf(v[2][0], w[6], fmaf(v[2][1], w[7], v[2][2] * w[8]));
+        ot[(oy * TS + ox) * HC + c] = __float2half_rn(a0 + a1 + a2);
+      }
     }
-#pragma unroll
-    for (int ox = 0; ox < TS; ++ox) {
-      float nc[3];
-      load_col(ox + 1, nc);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-      for (int ty = 0; ty < 3; ++ty) { v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty]; }
-      a0 = fmaf(v[0][0], w[0], fmaf(v[0][1], w[1], v[0][2] * w[2]));
-      a1 = fmaf(v[1][0], w[3], fmaf(v[1][1], w[4], v[1][2] * w[5]));
-      a2 = fmaf(v[2][0], w[6], fmaf(v[2][1], w[7], v[2][2] * w[8]));
-      ot[(oy * TS + ox) * HC + c] = __float2half_rn(a0 + a1 + a2);
-    }
-  }
+  };
+  if (interior) conv_items(std::true_type{});
+  else conv_items(std::false_type{});
   __syncthreads();
   if (LN) {
     constexpr int CIN = C + HC, KC = CIN / 8;
