@@ -225,6 +225,11 @@ def main():
     roof = None
     if rank == 0:
         eng = net.engine()
+        # the instrumented forward launches eagerly: release the CUDA graph (and its private activation pool -- 109 GiB for the
+        # 1080p one_len=96 Ours+ clip) first, the timed runs are over
+        _net._graphs = {}
+        out = o = None
+        torch.cuda.empty_cache()
         eng.timeline = []
         net(x_dev)
         torch.cuda.synchronize()
@@ -258,6 +263,15 @@ def main():
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("cab_pass_a_bytes_per_launch")
+        # the other kernels of the shift block, same accounting (algorithmic bytes of SURVEY.md section 8d / CUDA-event time):
+        # pass B reads z + shortcut and writes out (6C B/px; +2C where it also emits the next block's LayerNorm'd operand),
+        # the gather + conv1 + LayerNorm producer reads the rolled stream + the shifted half and writes the 1.5C-wide operand
+        other = {}
+        for nm, bpp in (("cab_pass_b", 6 * C + C), ("shift_conv1_ln", 2 * C + C + 3 * C), ("ln_planar", 5 * C)):
+            if nm in agg and agg[nm][1] > 0:
+                gbs = agg[nm][0] * bpp / (agg[nm][1] * 1e-3) / 1e9
+                other[nm] = {"bytes_per_pixel": bpp, "achieved": gbs, "frac": gbs / peak, "launches": agg[nm][2]}
+        roof["other_kernels"] = other
 
     if rank != 0:
         if dist is not None:
@@ -276,6 +290,7 @@ def main():
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 2,
                 "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches) * world,
+        "hbm_peak_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),     # rank 0, incl. the CUDA-graph pool
         "clocks": sampler.summary(),
         "roofline": roof,
     }

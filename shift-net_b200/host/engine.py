@@ -209,9 +209,16 @@ class Engine:
         enc2 = self.seq_cabs(p + ".encoder_level2", self.downsample(p + ".down12", enc1, c1, c2), c2)
         enc3 = self.seq_cabs(p + ".encoder_level3", self.downsample(p + ".down23", enc2, c2, c3), c3)
         dec3 = self.seq_cabs(p + ".decoder_level3", enc3, c3)
-        y = self.skip_upsample(p + ".up32", dec3, c3, self.cab(p + ".skip_attn2", enc2, c2), c2)
+        del enc3                      # intermediates are dropped as soon as their last consumer is enqueued: a 1080p
+        sk = self.cab(p + ".skip_attn2", enc2, c2)   # one_len=96 clip (BASELINE config K5) has 10 GB per full-res tensor
+        del enc2
+        y = self.skip_upsample(p + ".up32", dec3, c3, sk, c2)
+        del dec3, sk
         dec2 = self.seq_cabs(p + ".decoder_level2", y, c2)
-        y = self.skip_upsample(p + ".up21", dec2, c2, self.cab(p + ".skip_attn1", enc1, c1), c1)
+        sk = self.cab(p + ".skip_attn1", enc1, c1)
+        del enc1
+        y = self.skip_upsample(p + ".up21", dec2, c2, sk, c1)
+        del dec2, sk
         return self.seq_cabs(p + ".decoder_level1", y, c1)
 
     # ------------------------------------------------------------------ fused shift + NAF block
@@ -275,11 +282,13 @@ class Engine:
             L.check(self.lib.gsn_ln_pw(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
                                        1 if self.spec.circular else 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
                                        self._stream()), "ln_pw " + p)
+        del hw_pre
         ntl = self.lib.gsn_cab_tiles_linear(H * W)
         g = self._new(T, H, W, Cc)
         pg = self._new(T, ntl, Cc, dtype=torch.float32) if self.spec.denoise else None
         L.check(self.lib.gsn_dw_gate(ga.data_ptr(), gb.data_ptr(), T, H, W, Cc, wd.data_ptr(), g.data_ptr(),
                                      pg.data_ptr() if pg is not None else None, self._stream()), "dw_gate")
+        del ga, gb
         s1 = None
         if self.spec.denoise:        # mid CALayer2: its per-channel scale commutes with the grouped RepConv
             s1 = self._new(T, Cc, dtype=torch.float32)
@@ -289,12 +298,14 @@ class Engine:
         with self._timed("group_conv5", T * H * W):
             L.check(self.lib.gsn_group_conv5(g.data_ptr(), T, H, W, Cc, wfrag.data_ptr(),
                                              s1.data_ptr() if s1 is not None else None, u.data_ptr(), self._stream()), "group_conv5")
+        del g
         # second 1x1 (C -> 2C) + SimpleGate2 + per-tile sums in one kernel (u is read once, a|b never touch HBM)
         z = self._new(T, H, W, Cc)
         partial = self._new(T, ntl, Cc, dtype=torch.float32)
         with self._timed("cab_pass_a2", T * H * W):
             L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2p.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 0,
                                              self._stream()), "cab_pass_a2")
+        del u
         return self._fold_and_pass_b(p, x, z, partial, ntl, fw, mode)
 
     def shift_cab(self, p, x, c, reverse):
@@ -389,6 +400,8 @@ class Engine:
         if sp.plus:
             return self.stage1_plus(p, x)
         n0, c = sp.n0, sp.c1
+        if isinstance(x, list):       # [tensor]: the caller hands its only reference over, the input dies after the first CAB
+            x = x.pop()
         x = self.cab(p + ".concat", x, n0)
         shortcut = x
         y = self.conv(p + ".down01.0", [x], [n0], c, stride=2, pad=0, prelu_key=p + ".down01.1.weight")
@@ -416,6 +429,8 @@ class Engine:
         levels, shift blocks (C=80) on the way up."""
         sp = self.spec
         n0, c = sp.n0, sp.c1
+        if isinstance(x, list):
+            x = x.pop()
         x = self.cab(p + ".concat", x, n0)
         shortcut = x
         if sp.denoise:
@@ -432,10 +447,15 @@ class Engine:
         y = self.cab(p + ".encoder_level3_1", self.cab(p + ".encoder_level3", y, c), c)
         y = self.shift_block(p + ".decoder_level3", y)
         y = self.shift_block(p + ".decoder_level3_1", y)
-        y = self.skip_upsample(p + ".up32", y, c, self.cab(p + ".skip_attn2", enc22, c), c)
+        sk = self.cab(p + ".skip_attn2", enc22, c)
+        del enc22
+        y = self.skip_upsample(p + ".up32", y, c, sk, c)
         y = self.shift_block(p + ".decoder_level2", y)
         y = self.shift_block(p + ".decoder_level2_1", y)
-        y = self.skip_upsample(p + ".up21", y, c, self.cab(p + ".skip_attn1", enc11, c), c)
+        sk = self.cab(p + ".skip_attn1", enc11, c)
+        del enc11
+        y = self.skip_upsample(p + ".up21", y, c, sk, c)
+        del sk
         for n in ("decoder_level1", "decoder_level1_1", "decoder_level1_2"):
             y = self.shift_block(f"{p}.{n}", y)
         sk = self.cab(p + ".skip_conv", shortcut, n0)
@@ -473,6 +493,7 @@ class Engine:
         L.check(self.lib.gsn_conv_in(xin.data_ptr(), dt, T, cin, H, W, wi.data_ptr(), bi.data_ptr(), n0p, f0.data_ptr(),
                                      self._stream()), "conv_in")
         x0 = self.cab("feat_extract.1", f0, n0)
+        del f0
         # stage 0 (gshift_deblur2.py:731-737)
         f = x0
         for i in range(1, sp.n_orb + 1):
@@ -481,12 +502,20 @@ class Engine:
             f = self.add(f, x0)
         sam0 = f
         sam = self.conv("conv_trans", [f], [n0], n0)
-        dec = self.stage1("stage1", sam)
+        del f
+        holder = [sam]
+        if sp.denoise:
+            sam0 = None               # the denoise nets feed conv_trans' output to stage 2 (gshift_denoise2.py:752)
+        else:
+            sam = None                # deblur: stage 1 owns conv_trans' output from here on
+        dec = self.stage1("stage1", holder)
+        del holder
         # stage 2 on the centre frames only (gshift_deblur2.py:738-746,755)
         s = slice(past, T - future)
         third = sam[s] if sp.denoise else sam0[s]
         y = self.conv("rconcat", [x0[s], third, dec[s]], [n0, n0, n0], n0,
                       prelu_key="lrelu.weight" if sp.denoise else None)
+        del x0, third, dec, sam, sam0
         r = y
         for i in range(1, sp.n_orb + 1):
             r = self.tfr_unet(f"rorb{i}", r)
