@@ -147,8 +147,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry exactly ONE JSON line: NCCL writes its version banner to stdout at communicator creation
+        # (whatever NCCL_DEBUG says), so fd 1 points at stderr until the first collective has run
+        os.environ.pop("NCCL_DEBUG", None)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     GShiftNet = importlib.import_module("basicsr.models.archs." + args.arch).GShiftNet
     lib = pkg("host.lib").load()
