@@ -105,6 +105,33 @@ def test_cabi_exports_every_declared_symbol():
     assert handle.gsn_version() >= 100
 
 
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The descriptor structs of host/lib.py must have the size and field offsets the C compiler gives include/shiftnet_b200.h
+    (a silently shifted field would send garbage pointers to the kernels)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    lib_mod = importlib.import_module("shift-net_b200.host.lib")
+    pairs = [("GsnConvDesc", lib_mod.ConvDesc), ("GsnCabDense", lib_mod.CabDense), ("GsnCabPassA", lib_mod.CabPassA),
+             ("GsnCabPassB", lib_mod.CabPassB)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "shiftnet_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(gio.ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_product_path_never_imports_oracle():
     bad = []
     for d, _, files in os.walk(os.path.join(gio.ROOT, "shift-net_b200")):
