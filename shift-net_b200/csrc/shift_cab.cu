@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(1024) cab_fold_kernel(const float *__restrict_
 // pass B: out = shortcut + Weff_t z (+ beff)
 // ------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256, (C <= 64 ? 4 : 1)) cab_pass_b_kernel(const GsnCabPassB d) {
+__global__ void __launch_bounds__(256, (C <= 64 ? 4 : 3)) cab_pass_b_kernel(const GsnCabPassB d) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, NT = C / 8;
   extern __shared__ __align__(128) unsigned char smem_b[];
   unsigned char *sz = smem_b, *ss = smem_b + KC * PZ, *sw = smem_b + 2 * KC * PZ;
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(256) cab_fold_mid_kernel(const float *__restri
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) cab_pass_a2_kernel(const __half *__restrict__ u, const __half *__restrict__ w2eff,
+__global__ void __launch_bounds__(256, 3) cab_pass_a2_kernel(const __half *__restrict__ u, const __half *__restrict__ w2eff,
                                                           __half *__restrict__ z, float *__restrict__ chan_partial,
                                                           long long hw, size_t w_frame_stride /* halves; 0 = one weight for all frames */) {
   constexpr int MP = 128, KC = C / 8, PZ = (MP + 1) * 16, N = 2 * C, NTH = C / 8;
