@@ -530,6 +530,136 @@ __global__ void __launch_bounds__(256, (C <= 64 ? 2 : 1)) shift_conv1_kernel(con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same gather + conv1 + LayerNorm on 16x8-pixel tiles (C = 64): the 34x26 box + the 128-pixel conv tile are 65 KB and the
+// kernel fits 85 registers, so THREE CTAs are resident per SM instead of two -- the one-tile-per-CTA kernel is latency bound
+// (box wait at the head of every CTA, no pipe above 31 %), and occupancy is what hides that.  One conv item (channel, row) and
+// two LayerNorm pixels (as a quad of lanes) per thread; same arithmetic as shift_conv1_kernel<64, true, true>.
+__global__ void __launch_bounds__(256, 3) shift_conv1_ln_h8_kernel(const __half *__restrict__ x, int T, int H, int W, int mode, int circular,
+                                                                   const __half *__restrict__ wc1, __half *__restrict__ out,
+                                                                   const __grid_constant__ CUtensorMap tmap, const float *__restrict__ ln) {
+  constexpr int C = 64, HC = 32, TSX = 16, TSY = 8, BW = TSX + 18, BH = TSY + 18, CIN = C + HC, KC = CIN / 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __half *box = reinterpret_cast<__half *>(smem);                       // [BH*BW][HC]
+  __half *ot = reinterpret_cast<__half *>(smem + BH * BW * HC * 2);     // [TSY*TSX][HC]
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x, j = tid & 3;
+  const int t = blockIdx.z, x0 = blockIdx.x * TSX, y0 = blockIdx.y * TSY;
+  const RollSrc rs = roll_source(mode, circular, t, T, C);
+  const bool fwd = mode == GSN_MODE_CAB2_FWD;
+  const uint32_t bar_s = smem_u32(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    const int c0 = fwd ? rs.c_lo : rs.c_hi, f = fwd ? rs.f_lo : rs.f_hi;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_s), "r"(BW * BH * HC * 2) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::
+            "r"(smem_u32(box)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(x0 - 9), "r"(y0 - 9), "r"(f), "r"(bar_s)
+        : "memory");
+  }
+  // rolled stream of this thread's two LayerNorm pixels: requested now, consumed after the conv
+  uint4 rolled[2][2];
+  {
+    const size_t frame = (size_t)H * W * C;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int p = (tid >> 2) + it * 64, gy = y0 + p / TSX, gx = x0 + p % TSX;
+      rolled[it][0] = rolled[it][1] = make_uint4(0, 0, 0, 0);
+      if (gy < H && gx < W) {
+        const size_t pix = ((size_t)gy * W + gx) * C;
+        rolled[it][0] = __ldg(reinterpret_cast<const uint4 *>(x + rs.f_lo * frame + pix + rs.c_lo + j * 8));
+        rolled[it][1] = __ldg(reinterpret_cast<const uint4 *>(x + rs.f_hi * frame + pix + rs.c_hi + j * 8));
+      }
+    }
+  }
+  __syncthreads();          // barrier init visible before anyone polls it
+  {
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done) : "r"(bar_s) : "memory");
+      if (spin > (1 << 24)) __trap();     // a wrong tensor map must not hang the GPU
+    }
+  }
+  const bool interior = y0 >= 1 && y0 + TSY + 1 <= H && x0 >= 1 && x0 + TSX + 1 <= W;   // all destination taps in-image
+  auto conv_item = [&](auto int_tag) {
+    constexpr bool INT = decltype(int_tag)::value;
+    const int c = tid % HC, oy = tid / HC;       // HC * TSY == 256 items: one per thread
+    int dy, dx;
+    shift_offset<C>(c, dy, dx);
+    float w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = __half2float(__ldg(wc1 + i * HC + c));
+    const __half *rp = box + ((oy - 1 - dy + 9) * BW - dx + 9) * HC + c;   // (row oy+ty-1, col) -> rp[(ty*BW + col) * HC]
+    bool rowok[3];
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) { const int sy = y0 + oy + ty - 1; rowok[ty] = INT || (sy >= 0 && sy < H); }
+    float v[3][3];
+    auto load_col = [&](int col, float(&o)[3]) {
+      const int sx = x0 + col;
+      const bool cok = INT || (sx >= 0 && sx < W);
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) o[ty] = (INT || (cok && rowok[ty])) ? __half2float(rp[(ty * BW + col) * HC]) : 0.f;
+    };
+    {
+      float a[3], b[3];
+      load_col(-1, a);
+      load_col(0, b);
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) { v[ty][1] = a[ty]; v[ty][2] = b[ty]; }
+    }
+#pragma unroll
+    for (int ox = 0; ox < TSX; ++ox) {
+      float nc[3];
+      load_col(ox + 1, nc);
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) { v[ty][0] = v[ty][1]; v[ty][1] = v[ty][2]; v[ty][2] = nc[ty]; }
+      const float a0 = fmaf(v[0][0], w[0], fmaf(v[0][1], w[1], v[0][2] * w[2]));
+      const float a1 = fmaf(v[1][0], w[3], fmaf(v[1][1], w[4], v[1][2] * w[5]));
+      const float a2 = fmaf(v[2][0], w[6], fmaf(v[2][1], w[7], v[2][2] * w[8]));
+      ot[(oy * TSX + ox) * HC + c] = __float2half_rn(a0 + a1 + a2);
+    }
+  };
+  if (interior) conv_item(std::true_type{});
+  else conv_item(std::false_type{});
+  __syncthreads();
+  const size_t hw = (size_t)H * W;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int p = (tid >> 2) + it * 64, gy = y0 + p / TSX, gx = x0 + p % TSX;
+    float v[24];
+    unpack8(rolled[it][0], *reinterpret_cast<float(*)[8]>(&v[0]));
+    unpack8(rolled[it][1], *reinterpret_cast<float(*)[8]>(&v[8]));
+    unpack8(*reinterpret_cast<const uint4 *>(ot + (size_t)p * HC + j * 8), *reinterpret_cast<float(*)[8]>(&v[16]));
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { s4[i & 3] += v[i]; q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]); }
+    float sm = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float mu = sm * (1.f / CIN);
+    const float rstd = rsqrtf(fmaxf(ss * (1.f / CIN) - mu * mu, 0.f) + 1e-6f);
+    const float nmr = -mu * rstd;
+    if (gy < H && gx < W) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int ch = 4 * k + j;
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(ln + ch * 8)), g1 = __ldg(reinterpret_cast<const float4 *>(ln + ch * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ln + CIN + ch * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(ln + CIN + ch * 8 + 4));
+        const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[k * 8 + i], rstd, nmr), gam[i], bet[i]);
+        *reinterpret_cast<uint4 *>(out + (((size_t)t * KC + ch) * hw + (size_t)gy * W + gx) * 8) = pack8(o);
+      }
+    }
+  }
+}
+
 // y = clamped temporal roll of x (Shift_CAB.channel_shift, gshift_denoise1.py:167-179); C real channels inside cp
 __global__ void __launch_bounds__(256) roll_copy_kernel(const __half *__restrict__ x, __half *__restrict__ y, int T,
                                                         long long hw, int C, int cp, int reverse) {
@@ -606,6 +736,26 @@ extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int
   if (!encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34)) {
     set_error("shift_conv1_ln: cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", W, H, T);
     return GSN_E_CUDA;
+  }
+  static const bool h8 = [] { const char *e = getenv("GSN_SHIFT_H8"); return !(e && e[0] == '0'); }();
+  if (h8) {       // 16x8 tiles, three CTAs per SM
+    constexpr int smem8 = (34 * 26 + 16 * 8) * 32 * 2;
+    static bool attr8 = false;
+    if (!attr8) {
+      cudaFuncSetAttribute(shift_conv1_ln_h8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+      attr8 = true;
+    }
+    CUtensorMap tm8;
+    memset(&tm8, 0, sizeof(tm8));
+    if (!encode_tmap_nhwc(&tm8, x, C, W, H, T, C / 2, 34, 26)) {
+      set_error("shift_conv1_ln: cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", W, H, T);
+      return GSN_E_CUDA;
+    }
+    dim3 grid8((W + 15) / 16, (H + 7) / 8, T);
+    shift_conv1_ln_h8_kernel<<<grid8, 256, smem8, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half *>(x), T, H, W, mode, circular, reinterpret_cast<const __half *>(wc1), reinterpret_cast<__half *>(a1), tm8, ln);
+    count_launch();
+    return check_launch("shift_conv1_ln");
   }
   dim3 grid((W + 15) / 16, (H + 15) / 16, T);
   shift_conv1_kernel<64, true, true><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
