@@ -104,6 +104,18 @@ int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, int W, const 
 int gsn_conv_out(const void *src, int cp, int ks, const float *w, const void *resid, int cres, int x_dtype, int T, int H,
                  int W, void *dst, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * I/O side of the evaluation loop (inference/test_deblur_small.py:134-143,191-200).
+ * gsn_u8_to_clip: uint8 HWC frames (T,H,W,3), as read from disk and copied to the device unchanged, -> the (T,3,H,W) clip in
+ *   [0,1] with numpy2tensor's arithmetic: float32(u8) * float32(1/255), stored as fp16 or fp32.
+ * gsn_psnr_sse: partial[t][b] (b < gsn_psnr_sse_blocks()) = float64 partial sums of (clamp(out,0,1)*255 - gt)^2 over frame t,
+ *   out (T,3,H,W) fp16/fp32 as returned by the net, gt (T,H,W,3) uint8; the host adds the partials of a frame in index
+ *   order and finishes PSNR = 10 log10(255^2 / (sum / (3 H W))) -- skimage's peak_signal_noise_ratio(data_range=255).
+ * ------------------------------------------------------------------------------------------- */
+int gsn_u8_to_clip(const void *frames_u8, int T, int H, int W, int dtype, void *clip, void *stream);
+int gsn_psnr_sse_blocks(void);
+int gsn_psnr_sse(const void *out, int dtype, const void *gt_u8, int T, int H, int W, double *partial, void *stream);
+
 /* CALayer squeeze-excite MLP (d2:54-71): s[t][c] = sigmoid(W2 relu(W1 mean_hw)), from per-tile sums.
  * partial [T][ntiles][cp]; w1 fp32 [cr][c]; w2 fp32 [c][cr]; s fp32 [T][cp]. */
 int gsn_ca_scale(const float *partial, int ntiles, float inv_hw, const float *w1, const float *w2, int c, int cr, int cp,

@@ -93,14 +93,64 @@ def plan_units(videos, task, one_len):
     return units
 
 
-def to_tensor(frames):
-    """uint8 HWC list -> (1,T,3,H,W) float32 in [0,1]; cropped to multiples of 4 (test_deblur_small.py:124-128,191-200)."""
+def load_frames(frames):
+    """paths / arrays -> list of uint8 HWC arrays cropped to multiples of 4 (test_deblur_small.py:122-127)."""
     frames = [np.asarray(_imread(f) if isinstance(f, str) else f) for f in frames]
     h, w = frames[0].shape[:2]
     h, w = h - h % 4, w - w % 4
-    frames = [f[:h, :w] for f in frames]
-    t = torch.from_numpy(np.ascontiguousarray(np.stack(frames))).permute(0, 3, 1, 2).float().div_(255.0)
+    return [f[:h, :w] for f in frames]
+
+
+def to_tensor(frames):
+    """uint8 HWC list -> (1,T,3,H,W) float32 in [0,1] with numpy2tensor's arithmetic: float32(u8) * float32(1/255)
+    (test_deblur_small.py:191-200 -- a multiplication by the rounded reciprocal, not a division)."""
+    frames = load_frames(frames)
+    t = torch.from_numpy(np.ascontiguousarray(np.stack(frames))).permute(0, 3, 1, 2).float().mul_(1.0 / 255)
     return t.unsqueeze(0), frames
+
+
+class DeviceIO:
+    """The I/O side of the evaluation loop on the GPU: frames travel as uint8 from pinned host
+    memory (1 byte per sample), become the fp16 clip on the device (gsn_u8_to_clip), and the PSNR of every restored frame is
+    reduced on the device against the uint8 ground truth (gsn_psnr_sse): only 64 doubles per frame come back."""
+
+    def __init__(self, device):
+        import importlib
+        self.L = importlib.import_module("shift-net_b200.host.lib")
+        self.lib = self.L.load()
+        self.dev = device
+        self.nb = self.lib.gsn_psnr_sse_blocks()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def upload_u8(self, frames):
+        """list of uint8 HWC arrays -> (T,H,W,3) uint8 device tensor through pinned memory."""
+        host = torch.from_numpy(np.ascontiguousarray(np.stack(frames))).pin_memory()
+        return host.to(self.dev, non_blocking=True)
+
+    def clip_from_u8(self, frames_dev, dtype=torch.float16):
+        T, H, W, _ = frames_dev.shape
+        clip = torch.empty(1, T, 3, H, W, dtype=dtype, device=self.dev)
+        dt = self.L.DTYPE_F16 if dtype == torch.float16 else self.L.DTYPE_F32
+        self.L.check(self.lib.gsn_u8_to_clip(frames_dev.data_ptr(), T, H, W, dt, clip.data_ptr(), self._stream()), "u8_to_clip")
+        return clip
+
+    def psnr(self, out, gt_dev):
+        """out (T,3,H,W) fp16/fp32 as returned by the net, gt_dev (T,H,W,3) uint8 -> list of T PSNR values (float64)."""
+        T, _, H, W = out.shape
+        out = out.contiguous()
+        part = torch.empty(T, self.nb, dtype=torch.float64, device=self.dev)
+        dt = self.L.DTYPE_F16 if out.dtype == torch.float16 else self.L.DTYPE_F32
+        self.L.check(self.lib.gsn_psnr_sse(out.data_ptr(), dt, gt_dev.data_ptr(), T, H, W, part.data_ptr(), self._stream()), "psnr_sse")
+        res = []
+        for row in part.cpu().tolist():
+            sse = 0.0
+            for v in row:                 # fixed order: deterministic
+                sse += v
+            mse = sse / (3.0 * H * W)
+            res.append(float("inf") if mse == 0 else 10.0 * math.log10(255.0 ** 2 / mse))
+        return res
 
 
 def gather_records(records, device):
@@ -178,16 +228,29 @@ def run(net_cls, task, args):
     names = sorted(videos)
     units = plan_units(videos, task, getattr(args, "one_len", 0))
     records = []
+    dio = DeviceIO(device) if (use_cuda and not getattr(args, "cpu_io", False)) else None
     with torch.no_grad():
         for ui in range(rank, len(units), world):             # clip sharding: unit i -> rank i % world
             v, kk, in_seq, gt_seq = units[ui]
             t0 = time.time()
-            x, _ = to_tensor(in_seq)
-            _, gts = to_tensor(gt_seq)
-            T = x.shape[1]
-            if task == "deblur":
+            gpu_psnr = None
+            if task == "deblur" and dio is not None:
+                # device I/O path: uint8 H2D, /255 and the PSNR reduction on the GPU (SSIM stays on the host as in the reference)
+                ins, gts = load_frames(in_seq), load_frames(gt_seq)
+                x = dio.clip_from_u8(dio.upload_u8(ins))
+                T = x.shape[1]
+                out = net(x)
+                gpu_psnr = dio.psnr(out, dio.upload_u8(gts))
+                out = out.float()
+            elif task == "deblur":
+                x, _ = to_tensor(in_seq)
+                _, gts = to_tensor(gt_seq)
+                T = x.shape[1]
                 out = net(x.to(device).half()).float()
             else:
+                x, _ = to_tensor(in_seq)
+                _, gts = to_tensor(gt_seq)
+                T = x.shape[1]
                 sigma = args.sigma / 255.0
                 g = torch.Generator().manual_seed(1000 * names.index(v) + kk)
                 x = (x + sigma * torch.randn(x.shape, generator=g)).to(device).half()
@@ -205,7 +268,8 @@ def run(net_cls, task, args):
             imgs = (out.clamp(0, 1.0) * 255).permute(0, 2, 3, 1).cpu().numpy()
             base = kk * (T - 4)
             for e in range(imgs.shape[0]):
-                p, s = psnr_255(imgs[e], gts[e]), ssim_calculate(imgs[e], gts[e])
+                p = gpu_psnr[e] if gpu_psnr is not None else psnr_255(imgs[e], gts[e])
+                s = ssim_calculate(imgs[e], gts[e])
                 records.append((names.index(v), base + e, p, s))
                 if args.save_image:
                     import cv2
@@ -227,6 +291,7 @@ def add_common_args(parser):
     parser.add_argument("--data_path", type=str, default=None)
     parser.add_argument("--model_path", type=str, default=None)
     parser.add_argument("--result_path", type=str, default=None)
+    parser.add_argument("--cpu_io", action="store_true", help="reference-style host I/O: float conversion and PSNR on the CPU")
     parser.add_argument("--synthetic", type=int, default=0, help="number of synthetic videos (no dataset needed)")
     parser.add_argument("--synthetic_frames", type=int, default=12)
     parser.add_argument("--synthetic_h", type=int, default=64)

@@ -375,6 +375,43 @@ def test_full_size_cyclic_frame_equivariance(env):
     assert torch.equal(net(x), a)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_device_io_u8_clip_and_psnr(dtype):
+    """gsn_u8_to_clip is bit-exact against the reference's numpy2tensor arithmetic; gsn_psnr_sse reproduces the float64 PSNR of
+    clamp(out,0,1)*255 (float32, unrounded) against the uint8 ground truth (ragged size, values outside [0,1])."""
+    infer = gio.pkg("host.infer")
+    dio = infer.DeviceIO(torch.device(DEV))
+    g = np.random.default_rng(3)
+    T, H, W = 3, 37, 53
+    frames = [g.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(T)]
+    frames[0][:2] = 255; frames[0][2:4] = 0
+    clip = dio.clip_from_u8(dio.upload_u8(frames), dtype)
+    ref = torch.from_numpy(np.stack(frames)).permute(0, 3, 1, 2).float().mul_(1.0 / 255).to(dtype)
+    assert clip.shape == (1, T, 3, H, W) and torch.equal(clip[0].cpu(), ref)
+    out = (ref.float() + 0.05 * torch.from_numpy(g.standard_normal(ref.shape).astype(np.float32))).to(dtype)   # some values < 0 and > 1
+    gts = [g.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(T)]
+    got = dio.psnr(out.to(DEV), dio.upload_u8(gts))
+    imgs = (out.float().clamp(0, 1.0).permute(0, 2, 3, 1).numpy() * 255)
+    for e in range(T):
+        want = infer.psnr_255(imgs[e], gts[e])
+        assert abs(got[e] - want) <= 1e-9 * abs(want), (e, got[e], want)
+    same = dio.psnr(torch.from_numpy(np.stack(gts)).permute(0, 3, 1, 2).float().div(255).to(DEV), dio.upload_u8(gts))
+    assert all(p > 120 or p == float("inf") for p in same)     # float32 x/255*255 is exact or off by one ulp
+
+
+def test_inference_entry_point_device_io_matches_host_io(tmp_path):
+    """The deblur entry point with the device I/O path (default) and with --cpu_io print the same metrics."""
+    import subprocess
+    outs = []
+    for extra in ([], ["--cpu_io"]):
+        r = subprocess.run([sys.executable, os.path.join(gio.ROOT, "inference", "test_deblur_small.py"), "--synthetic", "1",
+                            "--one_len", "4", "--synthetic_frames", "8", "--result_path", str(tmp_path)] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("# ")])
+    assert outs[0] == outs[1] and len(outs[0]) == 2, outs
+
+
 def test_denoise_entry_point_synthetic(tmp_path):
     import subprocess
     r = subprocess.run([sys.executable, os.path.join(gio.ROOT, "inference", "test_denoise_small.py"), "--synthetic", "1",

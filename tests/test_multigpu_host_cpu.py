@@ -83,3 +83,20 @@ def test_metrics_formulas():
     assert abs(infer.psnr_255(a, b) - 10 * np.log10(255 ** 2 / mse)) < 1e-9
     assert infer.psnr_255(a, a) == float("inf")
     assert abs(infer.ssim_calculate(a, a) - 1.0) < 1e-6 and infer.ssim_calculate(a, b) < 1.0
+
+
+def test_to_tensor_matches_reference_numpy2tensor_arithmetic():
+    """inference/test_deblur_small.py:191-200: float32(u8) then mul_(1/255) -- a multiplication by the float32-rounded reciprocal.
+    All 256 byte values, through float32 and through the .half() the scripts apply."""
+    import numpy as np
+    import torch
+    infer = gio.pkg("host.infer")
+    img = np.arange(256, dtype=np.uint8).reshape(4, 64, 1).repeat(3, axis=2)          # HWC, H=4 W=64
+    ours, frames = infer.to_tensor([img])
+    ref = torch.from_numpy(np.ascontiguousarray(np.array(img).astype("float64").transpose((2, 0, 1)))).float()
+    ref.mul_(1.0 / 255)
+    assert torch.equal(ours[0, 0], ref) and torch.equal(ours.half()[0, 0], ref.half())
+    assert frames[0].dtype == np.uint8
+    # the CUDA kernel (gsn_u8_to_clip) computes float32(u8) * float32(1/255) with one rounding: the same values
+    k = np.float32(1.0 / 255.0)
+    assert np.array_equal((np.arange(256, dtype=np.float32) * k), ref[0].reshape(-1).numpy())
