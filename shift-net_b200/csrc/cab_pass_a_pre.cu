@@ -9,9 +9,10 @@
 //   * the LayerNorm (21 % of the tile time there, run on 1.89x the pixels because of the halo) leaves the issue-bound kernel;
 //   * the freed shared memory holds W1 and the phase-2 weights permanently (loaded once per CTA, also for CAB2);
 //   * GEMM1 of the NEXT tile is issued while the current tile is still in its CUDA-core stages: M tiles 2,3 (TMEM columns
-//     256..511, free once the accumulators were drained to shared memory) right after the depthwise stages, M tiles 0,1
-//     (columns 0..255, which GEMM2 uses) after the sigmoid gate -- the tensor core and the TMA run entirely under the
-//     CUDA-core work of the previous tile.
+//     256..511, free once the accumulators were drained to shared memory) right behind GEMM2, M tiles 0,1 (columns 0..255,
+//     which GEMM2 uses) as soon as the sigmoid gate has pulled GEMM2's output out of TMEM (named barrier, only the issuing
+//     warp waits) -- the tensor core and the TMA run under the CUDA-core work of the previous tile;
+//   * the z tile leaves through one swizzled TMA tile store.
 // Stages P3..P7 (TMEM -> G1, dw3x3 + gate, dw5x5, GEMM2, sigmoid gate, store + channel sums) are those of
 // cab_pass_a_tc.cu; reference semantics gshift_deblur2.py:186-258.
 #include <cstdlib>
