@@ -98,6 +98,14 @@ int gsn_cab_dense(const GsnCabDense *d, void *stream);
 int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, int W, const float *w, const float *bias,
                 int cout_p, void *dst, void *stream);
 
+/* The same conv for the denoise nets with the torch.cat((x, noise_map), 1) of gshift_denoise2.py:749 folded into the load:
+ * x holds the `cin` image channels, conv-input channel `cin` is read from noise_map (same dtype as x) at
+ * noise_map[t*nm_stride_t + y*nm_stride_y + x*nm_stride_x] (element strides; an expand()ed map has zero strides).
+ * w: fp32 [9][cin+1][cout_p]. */
+int gsn_conv_in_nm(const void *x, int x_dtype, int T, int cin, int H, int W, const void *noise_map, long long nm_stride_t,
+                   long long nm_stride_y, long long nm_stride_x, const float *w, const float *bias, int cout_p, void *dst,
+                   void *stream);
+
 /* Last conv: NHWC features -> NCHW frames + input residual. Replaces conv_last (d2:712,745) and the
  * "+ shortcut[num_fb:frames-num_ff]" of d2:756.  src (T,H,W,cp) fp16; w fp32 [ks*ks][cp][3];
  * resid/dst: (T,3,H,W) in x_dtype, resid has cres channels per frame (3, or 4 for the cat'ed denoise input). */
@@ -157,12 +165,12 @@ typedef struct {
                            RepConv).  A per-channel scale commutes with the depthwise RepConv, so with mid_ca=1 pass A
                            stops after the RepConv: ``z`` receives u = RepConv(gate) (C ch) and ``chan_partial`` the
                            per-tile sums of the gated tensor; gsn_cab_fold_mid + gsn_cab_pass_a2 finish the block. */
-  const void *hw_pre;   /* CAB2 modes: NULL = the shift gather + conv1 run inside pass A (bounding box in smem);
-                           non-NULL = (T,H,W,C/2) fp16 from gsn_shift_conv1, read in the LayerNorm load stage */
-  const void *a1_pre;   /* NULL = the LayerNorm (d2:209,250) runs inside pass A.  non-NULL = its output, precomputed by
-                           gsn_ln_planar in the k-chunk planar layout [T][CIN/8][H][W][8] fp16 (CIN = C for CAB1, 3C/2 for
-                           CAB2): pass A lands each tile's halo'd region with one TMA tile load directly in the tensor-core
-                           operand layout (cab_pass_a_pre.cu); x and hw_pre are not read then. */
+  const void *hw_pre;   /* unused by pass A (kept for ABI stability): (T,H,W,C/2) fp16 from gsn_shift_conv1 is consumed by
+                           gsn_ln_planar, which produces a1_pre */
+  const void *a1_pre;   /* REQUIRED: the LayerNorm (d2:209,250) output in the k-chunk planar layout [T][CIN/8][H][W][8] fp16
+                           (CIN = C for CAB1, 3C/2 for CAB2), produced by gsn_shift_conv1_ln (CAB2), by the epilogue of the
+                           preceding gsn_cab_pass_b (CAB1, GsnCabPassB.a1_next) or by gsn_ln_planar: pass A lands each tile's
+                           halo'd region with TMA tile loads directly in the tensor-core operand layout; x is not read. */
 } GsnCabPassA;
 
 int gsn_cab_tiles(int mode, int H, int W);
@@ -235,7 +243,8 @@ int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const 
                 void *stream);
 /* z = a * sigmoid(b) (SimpleGate2) + per-tile channel sums [T][tiles_linear][C]. */
 int gsn_gate2(const void *a, const void *b, int T, int H, int W, int C, void *out, float *partial, void *stream);
-/* u = (conv5x5 + conv3x3 + id)(g), groups of 8 channels, times an optional per-frame channel scale [T][C] (fp32).
+/* u = (conv5x5 + conv3x3 + id)(s * g), groups of 8 channels (RepConv, gshift_deblur1.py:157-165); s = optional per-frame
+ * channel scale [T][C] (fp32) of the denoise mid CALayer2 (gshift_denoise1.py:190-191,224-225), applied to the INPUT.
  * wfrag: merged 5x5 taps in mma B-fragment order [C/8][13][32 lanes][4] fp16 (host/packing.py pack_group_conv5). */
 int gsn_group_conv5(const void *g, int T, int H, int W, int C, const void *wfrag, const float *scale, void *out, void *stream);
 /* y = clamped half-channel temporal roll of x (Shift_CAB.channel_shift, gshift_denoise1.py:167-179); C real of cp channels. */

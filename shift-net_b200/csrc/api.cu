@@ -28,6 +28,34 @@ int check_launch(const char *what) {
   return GSN_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+bool device_needs_setup(unsigned long long *mask) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return true;      // beyond the mask: repeat the (idempotent, cheap) setup every call
+  return !(__atomic_load_n(mask, __ATOMIC_ACQUIRE) & (1ull << dev));
+}
+
+void device_setup_done(unsigned long long *mask) {
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64) __atomic_fetch_or(mask, 1ull << dev, __ATOMIC_RELEASE);
+}
+
 typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

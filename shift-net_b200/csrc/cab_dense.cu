@@ -260,12 +260,9 @@ cab_dense_kernel(const GsnCabDense d, const __grid_constant__ CUtensorMap tm_in,
 template <int CP, int R, int TH>
 static int launch_cab_dense(const GsnCabDense &d, cudaStream_t st) {
   using K = DenseCfg<CP, R, TH>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  GSN_ONCE_PER_DEVICE(
     cudaFuncSetAttribute(cab_dense_kernel<CP, R, TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    cudaFuncSetAttribute(cab_dense_kernel<CP, R, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    attr_set = true;
-  }
+    cudaFuncSetAttribute(cab_dense_kernel<CP, R, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
   CUtensorMap tm_in, tm_out;
   memset(&tm_in, 0, sizeof(tm_in));
   memset(&tm_out, 0, sizeof(tm_out));

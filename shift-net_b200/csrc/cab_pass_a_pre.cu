@@ -567,19 +567,10 @@ __global__ void __launch_bounds__(256) ln_planar_kernel(const __half *__restrict
 template <int KC1, bool MIDCA>
 static int launch_pass_a_pre(const GsnCabPassA &d, cudaStream_t st, const CUtensorMap &tm, const CUtensorMap &tm_z) {
   using K = PreCfg<KC1>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(cab_pass_a_pre_kernel<KC1, MIDCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    attr_set = true;
-  }
+  GSN_ONCE_PER_DEVICE(
+    cudaFuncSetAttribute(cab_pass_a_pre_kernel<KC1, MIDCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
   const long long total = (long long)((d.W + K::TW - 1) / K::TW) * ((d.H + K::TH - 1) / K::TH) * d.T;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_count();
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
   cab_pass_a_pre_kernel<KC1, MIDCA><<<grid, kPreThreads, K::SMEM, st>>>(d, tm, tm_z);
   count_launch();

@@ -267,15 +267,8 @@ int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st) {
     set_error("cab_pass_b: cuTensorMapEncodeTiled failed (H*W=%lld T=%d)", hw, d.T);
     return GSN_E_CUDA;
   }
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(cab_pass_b_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM); attr = true; }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(cab_pass_b_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+  const int num_sms = sm_count();
   const long long total = (hw + K::MP - 1) / K::MP * d.T;
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
   cab_pass_b_tc_kernel<<<grid, kPbThreads, K::SMEM, st>>>(d, tm_z, tm_x, tm_out);

@@ -22,6 +22,22 @@ bool encode_tmap_nhwc(CUtensorMap *tm, const void *base, int C, int W, int H, in
 // K-major UMMA operand layout.  Zero OOB fill.
 bool encode_tmap_planar(CUtensorMap *tm, const void *base, int W, int H, int KC, int T, int bw, int bh);
 
+// Kernel function attributes (cudaFuncSetAttribute) and the SM count are per DEVICE, not per process: one-time setup is
+// keyed by the current device.  The flag is published only after the setup ran, so a second host thread either repeats the
+// (idempotent) setup or sees it complete -- it never launches ahead of it.
+int current_device();
+int sm_count();                                    // multiprocessors of the current device (cached per device)
+bool device_needs_setup(unsigned long long *mask); // atomically reads the current device's bit
+void device_setup_done(unsigned long long *mask);
+#define GSN_ONCE_PER_DEVICE(...)                          \
+  do {                                                    \
+    static unsigned long long once_mask_ = 0;             \
+    if (gsn::device_needs_setup(&once_mask_)) {           \
+      __VA_ARGS__;                                        \
+      gsn::device_setup_done(&once_mask_);                \
+    }                                                     \
+  } while (0)
+
 #define GSN_REQUIRE(cond, ...)             \
   do {                                     \
     if (!(cond)) {                         \

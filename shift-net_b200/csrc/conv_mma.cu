@@ -214,11 +214,8 @@ static int launch_conv(const GsnConvDesc &d, cudaStream_t st) {
   const int pitch = d.cin_p + 8;
   const size_t smem = (size_t)IH * IW * pitch * 2 + 8 * d.cout_p * sizeof(float);
   if (smem > 227 * 1024) { set_error("conv_mma: tile needs %zu B smem", smem); return GSN_E_UNSUPPORTED; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv_mma_kernel<NT, KS, STRIDE, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
+  GSN_ONCE_PER_DEVICE(
+    cudaFuncSetAttribute(conv_mma_kernel<NT, KS, STRIDE, CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((d.Wout + 15) / 16, (d.Hout + 15) / 16, d.T);
   conv_mma_kernel<NT, KS, STRIDE, CINP><<<grid, 256, smem, st>>>(d);
   count_launch();

@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(320) gate_kernel(const __half *__restrict__ a,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// group_conv5: u = (conv5x5 + conv3x3 + id)(g) with groups of 8 channels, optional per-frame channel scale
-// (the denoise mid CALayer2 commutes with the grouped conv).  mma.sync m16n8k16: M = 16 pixels of a row, N = the 8
+// group_conv5: u = (conv5x5 + conv3x3 + id)(s * g) with groups of 8 channels; s = optional per-frame channel scale of the
+// denoise mid CALayer2, applied to the staged INPUT tile (it does not commute with a conv that mixes a group's channels).  mma.sync m16n8k16: M = 16 pixels of a row, N = the 8
 // outputs of one group, K = (2 taps) x (8 inputs); 13 k-steps cover the 25 taps (+1 zero tap).
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
@@ -308,6 +308,24 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
   }
   cp_async_commit();
   cp_async_wait<0>();
+  if (scale) {
+    // denoise: RepConv(s * g) (gshift_denoise1.py:190-191,224-225) -- a grouped conv mixes the 8 channels of a group, so the
+    // per-channel scale must sit on the INPUT side: each thread scales the pixels it staged itself (same p loop => its own
+    // cp.async data, already complete for this thread); the identity term below then reads s*g as well
+    const float4 *sc4 = reinterpret_cast<const float4 *>(scale + (size_t)t * C);
+    for (int p = tid; p < TW * TW; p += 256) {
+#pragma unroll
+      for (int ch = 0; ch < NG; ++ch) {
+        uint4 *q = reinterpret_cast<uint4 *>(tile + (size_t)p * PITCH + ch * 8);
+        const float4 s0 = __ldg(sc4 + ch * 2), s1 = __ldg(sc4 + ch * 2 + 1);
+        float f[8];
+        unpack8(*q, f);
+        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+        *q = pack8(f);
+      }
+    }
+  }
   __syncthreads();
 
   float acc[2][NG][4];
@@ -349,11 +367,7 @@ __global__ void __launch_bounds__(256, 2) group_conv5_kernel(const __half *__res
 #pragma unroll
       for (int n = 0; n < NG; ++n) {
         const float2 idv = unpack_half2(*reinterpret_cast<const uint32_t *>(cp + n * 8));
-        float v0 = acc[m][n][hrow * 2] + idv.x, v1 = acc[m][n][hrow * 2 + 1] + idv.y;
-        if (scale) {
-          v0 *= __ldg(scale + (size_t)t * C + n * 8 + tig * 2);
-          v1 *= __ldg(scale + (size_t)t * C + n * 8 + tig * 2 + 1);
-        }
+        const float v0 = acc[m][n][hrow * 2] + idv.x, v1 = acc[m][n][hrow * 2 + 1] + idv.y;
         *reinterpret_cast<uint32_t *>(dp + n * 8) = pack_half2(v0, v1);
       }
     }
@@ -689,14 +703,11 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   GSN_REQUIRE(mode == GSN_MODE_CAB2_FWD || mode == GSN_MODE_CAB2_REV, "shift_conv1: mode=%d is not a shift mode", mode);
   if (C != 64 && C != 80) { set_error("shift_conv1: C=%d unsupported (64, 80)", C); return GSN_E_UNSUPPORTED; }
   const int smem = (34 * 34 + 16 * 16) * (C / 2) * 2;
-  static bool attr = false;
-  if (!attr) {
+  GSN_ONCE_PER_DEVICE(
     cudaFuncSetAttribute(shift_conv1_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 32 * 2);
     cudaFuncSetAttribute(shift_conv1_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 32 * 2);
     cudaFuncSetAttribute(shift_conv1_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 40 * 2);
-    cudaFuncSetAttribute(shift_conv1_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 40 * 2);
-    attr = true;
-  }
+    cudaFuncSetAttribute(shift_conv1_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (34 * 34 + 16 * 16) * 40 * 2));
   dim3 grid((W + 15) / 16, (H + 15) / 16, T);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // TMA path: a 4-D tensor map (C, W, H, T) over x with a (C/2, 34, 34, 1) box; GSN_SHIFT_TMA=0 selects the cp.async loader
@@ -726,11 +737,7 @@ extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int
   GSN_REQUIRE(mode == GSN_MODE_CAB2_FWD || mode == GSN_MODE_CAB2_REV, "shift_conv1_ln: mode=%d is not a shift mode", mode);
   if (C != 64) { set_error("shift_conv1_ln: C=%d unsupported (64)", C); return GSN_E_UNSUPPORTED; }
   constexpr int smem = (34 * 34 + 16 * 16) * 32 * 2;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(shift_conv1_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(shift_conv1_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   if (!encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34)) {
@@ -740,11 +747,7 @@ extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int
   static const bool h8 = [] { const char *e = getenv("GSN_SHIFT_H8"); return !(e && e[0] == '0'); }();
   if (h8) {       // 16x8 tiles, three CTAs per SM
     constexpr int smem8 = (34 * 26 + 16 * 8) * 32 * 2;
-    static bool attr8 = false;
-    if (!attr8) {
-      cudaFuncSetAttribute(shift_conv1_ln_h8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
-      attr8 = true;
-    }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(shift_conv1_ln_h8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
     CUtensorMap tm8;
     memset(&tm8, 0, sizeof(tm8));
     if (!encode_tmap_nhwc(&tm8, x, C, W, H, T, C / 2, 34, 26)) {
@@ -789,8 +792,7 @@ extern "C" int gsn_ln_pw(const void *x, const void *hw_pre, int T, int H, int W,
   const long long hw = (long long)H * W;
   const int kc = (mode == GSN_MODE_CAB1 ? C : C + C / 2) / 8, kcp = (kc + 1) / 2 * 2;
   const int smem = 16 * 129 * 16 + std::max(kcp * 2 * C * 16, 2 * C / 8 * 129 * 16);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(ln_pw_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16 + 20 * 129 * 16); attr = true; }
+  GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(ln_pw_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16 + 20 * 129 * 16));
   dim3 grid((unsigned)((hw + 127) / 128), T);
   ln_pw_kernel<80><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half *>(x), reinterpret_cast<const __half *>(hw_pre), T, hw, mode, circular, ln,
@@ -835,8 +837,7 @@ extern "C" int gsn_group_conv5(const void *g, int T, int H, int W, int C, const 
   dim3 grid((W + 15) / 16, (H + 15) / 16, T);
   if (C == 80) {
     const size_t smem = 20 * 20 * (80 + 8) * 2;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(group_conv5_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(group_conv5_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     group_conv5_kernel<80><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(g), H, W,
                                                     reinterpret_cast<const uint2 *>(wfrag), scale, reinterpret_cast<__half *>(out));
   } else {

@@ -10,11 +10,15 @@ namespace gsn {
 template <typename TIn, int COUT_P>
 __global__ void __launch_bounds__(256) conv_in_kernel(const TIn *__restrict__ x, int T, int cin, int H, int W,
                                                       const float *__restrict__ w, const float *__restrict__ bias,
-                                                      __half *__restrict__ dst) {
+                                                      __half *__restrict__ dst, const TIn *__restrict__ nm = nullptr,
+                                                      long long nm_st = 0, long long nm_sy = 0, long long nm_sx = 0) {
+  // nm != null: the denoise nets' torch.cat((x, noise_map), 1) (gshift_denoise2.py:749) folded into the load -- channel `cin` of
+  // the conv input is read from the (possibly expand()ed, i.e. zero-stride) noise map instead of a concatenated copy
   __shared__ __align__(16) float sw[9 * 4 * COUT_P];
   __shared__ __align__(16) float sb[COUT_P];
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < 9 * cin * COUT_P; i += 256) sw[i] = w[i];
+  const int cw = cin + (nm ? 1 : 0);      // channels of the conv weight
+  for (int i = tid; i < 9 * cw * COUT_P; i += 256) sw[i] = w[i];
   if (tid < COUT_P) sb[tid] = bias ? bias[tid] : 0.f;
   __syncthreads();
   const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y, t = blockIdx.z;
@@ -32,7 +36,17 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const TIn *__restrict__ x,
       if (xx < 0 || xx >= W) continue;
       for (int ci = 0; ci < cin; ++ci) {
         const float v = (float)xt[ci * plane + (size_t)yy * W + xx];
-        const float4 *wr = reinterpret_cast<const float4 *>(sw + ((ky * 3 + kx) * cin + ci) * COUT_P);
+        const float4 *wr = reinterpret_cast<const float4 *>(sw + ((ky * 3 + kx) * cw + ci) * COUT_P);
+#pragma unroll
+        for (int q = 0; q < COUT_P / 4; ++q) {
+          const float4 ww = wr[q];
+          acc[q * 4 + 0] += v * ww.x; acc[q * 4 + 1] += v * ww.y;
+          acc[q * 4 + 2] += v * ww.z; acc[q * 4 + 3] += v * ww.w;
+        }
+      }
+      if (nm) {
+        const float v = (float)nm[t * nm_st + yy * nm_sy + xx * nm_sx];
+        const float4 *wr = reinterpret_cast<const float4 *>(sw + ((ky * 3 + kx) * cw + cin) * COUT_P);
 #pragma unroll
         for (int q = 0; q < COUT_P / 4; ++q) {
           const float4 ww = wr[q];
@@ -101,33 +115,44 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __half *__restrict_
 
 }  // namespace gsn
 
-extern "C" int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, int W, const float *w, const float *bias,
-                           int cout_p, void *dst, void *stream) {
+static int conv_in_impl(const void *x, int x_dtype, int T, int cin, int H, int W, const void *nm, long long nm_st, long long nm_sy,
+                        long long nm_sx, const float *w, const float *bias, int cout_p, void *dst, void *stream) {
   using namespace gsn;
   GSN_REQUIRE(x && w && dst, "conv_in: null pointer");
-  GSN_REQUIRE(cin >= 1 && cin <= 4, "conv_in: cin=%d (expected 3 or 4)", cin);
+  GSN_REQUIRE(cin >= 1 && cin + (nm ? 1 : 0) <= 4, "conv_in: cin=%d (expected 3, or 3 + noise map, or 4)", cin);
   GSN_REQUIRE(T > 0 && H > 0 && W > 0, "conv_in: empty shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((W + 31) / 32, (H + 7) / 8, T), block(32, 8);
   __half *d = reinterpret_cast<__half *>(dst);
-  if (cout_p == 16 && x_dtype == GSN_DTYPE_F16)
-    conv_in_kernel<__half, 16><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
-  else if (cout_p == 16 && x_dtype == GSN_DTYPE_F32)
-    conv_in_kernel<float, 16><<<grid, block, 0, st>>>((const float *)x, T, cin, H, W, w, bias, d);
-  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F16)
-    conv_in_kernel<__half, 24><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
-  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F32)
-    conv_in_kernel<float, 24><<<grid, block, 0, st>>>((const float *)x, T, cin, H, W, w, bias, d);
-  else if (cout_p == 32 && x_dtype == GSN_DTYPE_F16)
-    conv_in_kernel<__half, 32><<<grid, block, 0, st>>>((const __half *)x, T, cin, H, W, w, bias, d);
-  else if (cout_p == 32 && x_dtype == GSN_DTYPE_F32)
-    conv_in_kernel<float, 32><<<grid, block, 0, st>>>((const float *)x, T, cin, H, W, w, bias, d);
+#define GSN_CI(TIN, CP) conv_in_kernel<TIN, CP><<<grid, block, 0, st>>>((const TIN *)x, T, cin, H, W, w, bias, d, (const TIN *)nm, nm_st, nm_sy, nm_sx)
+  if (cout_p == 16 && x_dtype == GSN_DTYPE_F16) GSN_CI(__half, 16);
+  else if (cout_p == 16 && x_dtype == GSN_DTYPE_F32) GSN_CI(float, 16);
+  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F16) GSN_CI(__half, 24);
+  else if (cout_p == 24 && x_dtype == GSN_DTYPE_F32) GSN_CI(float, 24);
+  else if (cout_p == 32 && x_dtype == GSN_DTYPE_F16) GSN_CI(__half, 32);
+  else if (cout_p == 32 && x_dtype == GSN_DTYPE_F32) GSN_CI(float, 32);
   else {
     set_error("conv_in: cout_p=%d dtype=%d unsupported", cout_p, x_dtype);
     return GSN_E_UNSUPPORTED;
   }
+#undef GSN_CI
   count_launch();
   return check_launch("conv_in");
+}
+
+extern "C" int gsn_conv_in(const void *x, int x_dtype, int T, int cin, int H, int W, const float *w, const float *bias,
+                           int cout_p, void *dst, void *stream) {
+  return conv_in_impl(x, x_dtype, T, cin, H, W, nullptr, 0, 0, 0, w, bias, cout_p, dst, stream);
+}
+
+extern "C" int gsn_conv_in_nm(const void *x, int x_dtype, int T, int cin, int H, int W, const void *noise_map, long long nm_stride_t,
+                              long long nm_stride_y, long long nm_stride_x, const float *w, const float *bias, int cout_p, void *dst,
+                              void *stream) {
+  if (!noise_map) {
+    gsn::set_error("conv_in_nm: null noise map");
+    return GSN_E_BADARG;
+  }
+  return conv_in_impl(x, x_dtype, T, cin, H, W, noise_map, nm_stride_t, nm_stride_y, nm_stride_x, w, bias, cout_p, dst, stream);
 }
 
 extern "C" int gsn_conv_out(const void *src, int cp, int ks, const float *w, const void *resid, int cres, int x_dtype,

@@ -24,341 +24,6 @@ namespace gsn {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------------
-// pass A
-// ------------------------------------------------------------------------------------------------
-template <int C, bool SHIFT, int TH>
-struct PassACfg {
-  static constexpr int TW = 16;
-  static constexpr int HC = C / 2;                  // shifted half
-  static constexpr int CIN = SHIFT ? C + HC : C;    // LayerNorm / first 1x1 input width
-  static constexpr int KC1 = CIN / 8;               // k-chunks of GEMM1
-  static constexpr int KC2 = C / 8;                 // k-chunks of GEMM2 (= gated chunks)
-  static constexpr int R1W = TW + 6, R1H = TH + 6;  // region where the 2C tensor is needed (3 px halo)
-  static constexpr int M1 = R1W * R1H;
-  static constexpr int M1P = (M1 + 15) / 16 * 16;
-  static constexpr int R2W = TW + 4, R2H = TH + 4;  // gated region (2 px halo for the 5x5)
-  static constexpr int M2 = R2W * R2H;
-  static constexpr int M3 = TW * TH;
-  static constexpr int BW = TW + 24, BH = TH + 24;  // bounding box of the shift gather (3 + 1 + 8 px halo)
-  // weight blob (bytes); must match host/packing.py
-  static constexpr int OFF_LN = 0;                              // gamma[CIN], beta[CIN] fp32
-  static constexpr int OFF_C1 = OFF_LN + 2 * CIN * 4;           // conv1 dw3x3 [9][HC] fp16 (SHIFT only)
-  static constexpr int OFF_W1 = OFF_C1 + (SHIFT ? 9 * HC * 2 : 0);  // [KC1][2C][8] fp16
-  static constexpr int OFF_DA = OFF_W1 + KC1 * 2 * C * 16;      // dw3x3 on 2C ch: [9][2C] fp16
-  static constexpr int OFF_DB = OFF_DA + 9 * 2 * C * 2;         // merged 5x5 (+3x3) on C ch: [25][C] fp16
-  static constexpr int OFF_W2 = OFF_DB + 25 * C * 2;            // [KC2][2C][8] fp16
-  static constexpr int BLOB = OFF_W2 + KC2 * 2 * C * 16;
-  // shared memory map (bytes)
-  static constexpr int P1 = (M1P + 1) * 16;                     // plane pitches
-  static constexpr int P2 = (M2 + 1) * 16;
-  static constexpr int P3 = (M3 + 1) * 16;
-  static constexpr int S_WB = 0;
-  static constexpr int S_A1 = (BLOB + 127) / 128 * 128;
-  static constexpr int A1_BYTES = KC1 * P1;
-  static constexpr int S_UN = S_A1 + (A1_BYTES + 127) / 128 * 128;
-  static constexpr int R12_BYTES = SHIFT ? BW * BH * HC * 2 : 0;
-  static constexpr int G1S_BYTES = 4 * P1;                      // one slab: 2 a-chunks + 2 b-chunks
-  static constexpr int GT_BYTES = KC2 * P2;
-  static constexpr int UN_BYTES = (R12_BYTES > G1S_BYTES + GT_BYTES) ? R12_BYTES : (G1S_BYTES + GT_BYTES);
-  static constexpr int S_G1S = S_UN;
-  static constexpr int S_GT = S_UN + G1S_BYTES;
-  static constexpr int S_RED = S_UN + (UN_BYTES + 127) / 128 * 128;
-  static constexpr int SMEM = S_RED + 8 * C * 4;
-  static_assert(KC2 * P3 <= A1_BYTES, "A2 aliases A1");
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
-};
-
-__device__ __forceinline__ void fma8(float (&acc)[8], const uint4 &x, const uint4 &w) {
-  float a[8], b[8];
-  unpack8(x, a);
-  unpack8(w, b);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = fmaf(a[i], b[i], acc[i]);
-}
-
-template <int C, bool SHIFT, int TH>
-__global__ void __launch_bounds__(kThreads, 1) cab_pass_a_kernel(const GsnCabPassA d, const ShiftTable tab) {
-  using K = PassACfg<C, SHIFT, TH>;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t = blockIdx.z, x0 = blockIdx.x * K::TW, y0 = blockIdx.y * TH;
-  const __half *xg = reinterpret_cast<const __half *>(d.x);
-  const RollSrc rs = roll_source(d.mode, d.circular, t, d.T, C);
-  const size_t frame = (size_t)d.H * d.W * C;
-
-  // ---- P0: weights blob (+ gather bounding box) -> smem -----------------------------------------
-  {
-    const unsigned char *wb = reinterpret_cast<const unsigned char *>(d.wblob);
-    for (int i = tid; i < K::BLOB / 16; i += kThreads) cp_async16(smem + K::S_WB + i * 16, wb + i * 16, true);
-    if (SHIFT) {
-      // shifted half comes from the neighbour frame: low half (fwd) or high half (rev) of the rolled stream
-      const bool fwd = d.mode == GSN_MODE_CAB2_FWD;
-      const __half *src = xg + (size_t)(fwd ? rs.f_lo : rs.f_hi) * frame + (fwd ? rs.c_lo : rs.c_hi);
-      constexpr int CH = K::HC / 8;
-      for (int i = tid; i < K::BW * K::BH * CH; i += kThreads) {
-        const int ch = i % CH, p = i / CH, by = p / K::BW, bx = p - by * K::BW;
-        const int gy = y0 - 12 + by, gx = x0 - 12 + bx;
-        const bool valid = gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
-        const __half *sp = valid ? src + ((size_t)gy * d.W + gx) * C + ch * 8 : src;
-        cp_async16(smem + K::S_UN + (size_t)p * K::HC * 2 + ch * 16, sp, valid);
-      }
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-  }
-
-  // ---- P1: (shift gather + conv1) + LayerNorm -> A1 ----------------------------------------------
-  {
-    const float *ln_g = reinterpret_cast<const float *>(smem + K::S_WB + K::OFF_LN);
-    const float *ln_b = ln_g + K::CIN;
-    const __half *wc1 = reinterpret_cast<const __half *>(smem + K::S_WB + K::OFF_C1);
-    const __half *r12 = reinterpret_cast<const __half *>(smem + K::S_UN);
-    constexpr int NV = SHIFT ? 24 : 16;  // values per lane of the pixel quad
-    for (int item = tid; item < K::M1P * 4; item += kThreads) {
-      const int q = item >> 2, j = item & 3;
-      const int ry = q / K::R1W, rx = q - ry * K::R1W;
-      const int gy = y0 - 3 + ry, gx = x0 - 3 + rx;
-      const bool inimg = (q < K::M1) && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
-      float v[NV];
-      int chunk_of[NV / 8];
-      if (inimg) {
-        const size_t pix = ((size_t)gy * d.W + gx) * C;
-        if (SHIFT) {
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_lo * frame + pix + rs.c_lo + j * 8)), *reinterpret_cast<float(*)[8]>(&v[0]));
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + rs.f_hi * frame + pix + rs.c_hi + j * 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
-          chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j;
-          // conv1 (dw3x3, zero pad) over the spatially shifted half, channels 8j..8j+7
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = j * 8 + i;
-            const int dy = tab.dy[c], dx = tab.dx[c];
-            float a = 0.f;
-#pragma unroll
-            for (int ty = -1; ty <= 1; ++ty)
-#pragma unroll
-              for (int tx = -1; tx <= 1; ++tx) {
-                const int sy = gy + ty, sx = gx + tx;  // position in the shifted tensor (must be in-image)
-                if (sy < 0 || sy >= d.H || sx < 0 || sx >= d.W) continue;
-                const int by = ry + ty - dy + 9, bx = rx + tx - dx + 9;  // source position inside the bounding box
-                const float s = __half2float(r12[(by * K::BW + bx) * K::HC + c]);
-                a = fmaf(s, __half2float(wc1[((ty + 1) * 3 + tx + 1) * K::HC + c]), a);
-              }
-            v[16 + i] = a;
-          }
-        } else {
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16)), *reinterpret_cast<float(*)[8]>(&v[0]));
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(xg + (size_t)t * frame + pix + j * 16 + 8)), *reinterpret_cast<float(*)[8]>(&v[8]));
-          chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = 0.f;
-        if (SHIFT) { chunk_of[0] = j; chunk_of[1] = K::HC / 8 + j; chunk_of[2] = C / 8 + j; }
-        else { chunk_of[0] = 2 * j; chunk_of[1] = 2 * j + 1; }
-      }
-      // LayerNorm over the CIN channels of the pixel (quad reduction), biased variance, eps 1e-6 (d2:19-28)
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) s += v[i];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      const float mu = s * (1.f / K::CIN);
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { const float e = v[i] - mu; ss = fmaf(e, e, ss); }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      const float rstd = rsqrtf(ss * (1.f / K::CIN) + 1e-6f);
-#pragma unroll
-      for (int k = 0; k < NV / 8; ++k) {
-        float o[8];
-        const int cbase = chunk_of[k] * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = inimg ? (v[k * 8 + i] - mu) * rstd * ln_g[cbase + i] + ln_b[cbase + i] : 0.f;
-        *reinterpret_cast<uint4 *>(smem + K::S_A1 + chunk_of[k] * K::P1 + q * 16) = pack8(o);
-      }
-    }
-    __syncthreads();
-  }
-  if (d.debug_stage == 1) {
-    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC1 * K::M1P;
-    for (int i = tid; i < K::KC1 * K::M1P; i += kThreads)
-      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A1 + (i / K::M1P) * K::P1 + (i % K::M1P) * 16);
-  }
-
-  // ---- P2: GEMM1 (CIN -> 2C) in 4 channel slabs, each followed by dw3x3 + id and the gate ---------
-  const int g = lane >> 2, tig = lane & 3;
-  const uint32_t a1_s = smem_u32(smem + K::S_A1);
-  const uint32_t w1_s = smem_u32(smem + K::S_WB + K::OFF_W1);
-  constexpr int NSLAB = C / 16;  // each slab: 16 'a' channels + the 16 matching 'b' channels
-  for (int slab = 0; slab < NSLAB; ++slab) {
-    for (int mt = warp; mt < K::M1P / 16; mt += 8) {
-      float acc[4][4];
-#pragma unroll
-      for (int n = 0; n < 4; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int k = 0; k < K::KC1 / 2; ++k) {
-        uint32_t a[4];
-        ldmatrix_x4(a[0], a[1], a[2], a[3], a1_s + (2 * k + (lane >> 4)) * K::P1 + (mt * 16 + (lane & 15)) * 16);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {  // half 0: 'a' n-tiles (2*slab, 2*slab+1); half 1: 'b' n-tiles (+C/8)
-          const int n0 = (half * (C / 8) + 2 * slab) * 8;
-          uint32_t b[4];
-          ldmatrix_x4(b[0], b[1], b[2], b[3],
-                      w1_s + ((2 * k + ((lane >> 3) & 1)) * (2 * C) + n0 + (lane & 7) + ((lane >> 4) & 1) * 8) * 16);
-          mma16816(acc[half * 2 + 0], a, b[0], b[1]);
-          mma16816(acc[half * 2 + 1], a, b[2], b[3]);
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        unsigned char *pl = smem + K::S_G1S + n * K::P1 + tig * 4;
-        *reinterpret_cast<uint32_t *>(pl + (mt * 16 + g) * 16) = pack_half2(acc[n][0], acc[n][1]);
-        *reinterpret_cast<uint32_t *>(pl + (mt * 16 + g + 8) * 16) = pack_half2(acc[n][2], acc[n][3]);
-      }
-    }
-    __syncthreads();
-    // dw3x3 + identity on both halves, then SimpleGate (d2:169-181); GATED is forced to 0 outside the image
-    {
-      const unsigned char *wda = smem + K::S_WB + K::OFF_DA;
-      for (int item = tid; item < 2 * K::M2; item += kThreads) {
-        const int jj = item / K::M2, p = item - jj * K::M2;
-        const int ry = p / K::R2W, rx = p - ry * K::R2W;
-        const int gy = y0 - 2 + ry, gx = x0 - 2 + rx;
-        float o[8];
-        if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) {
-          float aa[8], bb[8];
-          const int ca = 2 * slab + jj, cb = C / 8 + 2 * slab + jj;  // chunk ids inside the 2C tensor
-          const unsigned char *pa = smem + K::S_G1S + jj * K::P1;
-          const unsigned char *pb = smem + K::S_G1S + (2 + jj) * K::P1;
-          const int ctr = (ry + 1) * K::R1W + rx + 1;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) aa[i] = bb[i] = 0.f;   // the "+ x" of RepConv2 is folded into the centre tap (host/packing.py)
-#pragma unroll
-          for (int ty = 0; ty < 3; ++ty)
-#pragma unroll
-            for (int tx = 0; tx < 3; ++tx) {
-              const int idx = (ry + ty) * K::R1W + rx + tx;
-              const int tap = ty * 3 + tx;
-              fma8(aa, *reinterpret_cast<const uint4 *>(pa + idx * 16), *reinterpret_cast<const uint4 *>(wda + (tap * 2 * C + ca * 8) * 2));
-              fma8(bb, *reinterpret_cast<const uint4 *>(pb + idx * 16), *reinterpret_cast<const uint4 *>(wda + (tap * 2 * C + cb * 8) * 2));
-            }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = aa[i] * bb[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        }
-        *reinterpret_cast<uint4 *>(smem + K::S_GT + (2 * slab + jj) * K::P2 + p * 16) = pack8(o);
-      }
-    }
-    __syncthreads();
-  }
-  if (d.debug_stage == 2) {
-    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M2;
-    for (int i = tid; i < K::KC2 * K::M2; i += kThreads)
-      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_GT + (i / K::M2) * K::P2 + (i % K::M2) * 16);
-  }
-
-  // ---- P3: dw5x5 + dw3x3 + id (RepConv, d2:159-168; the 3x3 is pre-merged into the 5x5 taps) -> A2 ----
-  {
-    const unsigned char *wdb = smem + K::S_WB + K::OFF_DB;
-    for (int item = tid; item < K::KC2 * K::M3; item += kThreads) {
-      const int ch = item / K::M3, p = item - ch * K::M3;
-      const int oy = p / K::TW, ox = p - oy * K::TW;
-      const unsigned char *pg = smem + K::S_GT + ch * K::P2;
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;             // identity folded into the centre tap
-#pragma unroll
-      for (int ty = 0; ty < 5; ++ty)
-#pragma unroll
-        for (int tx = 0; tx < 5; ++tx)
-          fma8(acc, *reinterpret_cast<const uint4 *>(pg + ((oy + ty) * K::R2W + ox + tx) * 16),
-               *reinterpret_cast<const uint4 *>(wdb + ((ty * 5 + tx) * C + ch * 8) * 2));
-      *reinterpret_cast<uint4 *>(smem + K::S_A1 + ch * K::P3 + p * 16) = pack8(acc);
-    }
-    __syncthreads();
-  }
-  if (d.debug_stage == 3) {
-    uint4 *o = reinterpret_cast<uint4 *>(d.debug_out) +
-               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * K::KC2 * K::M3;
-    for (int i = tid; i < K::KC2 * K::M3; i += kThreads)
-      o[i] = *reinterpret_cast<uint4 *>(smem + K::S_A1 + (i / K::M3) * K::P3 + (i % K::M3) * 16);
-  }
-
-  // ---- P4: GEMM2 (C -> 2C) + a*sigmoid(b) (SimpleGate2, d2:182-185) -> z, per-tile channel sums --------
-  {
-    const uint32_t a2_s = smem_u32(smem + K::S_A1);
-    const uint32_t w2_s = smem_u32(smem + K::S_WB + K::OFF_W2);
-    constexpr int NTH = C / 8;  // n-tiles per half
-    float csum[NTH][2];
-#pragma unroll
-    for (int n = 0; n < NTH; ++n) csum[n][0] = csum[n][1] = 0.f;
-    __half *zg = reinterpret_cast<__half *>(d.z) + (size_t)t * frame;
-    for (int mt = warp; mt < K::M3 / 16; mt += 8) {
-      float acc[2 * NTH][4];
-#pragma unroll
-      for (int n = 0; n < 2 * NTH; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int k = 0; k < K::KC2 / 2; ++k) {
-        uint32_t a[4];
-        ldmatrix_x4(a[0], a[1], a[2], a[3], a2_s + (2 * k + (lane >> 4)) * K::P3 + (mt * 16 + (lane & 15)) * 16);
-#pragma unroll
-        for (int np = 0; np < NTH; ++np) {  // pairs of n-tiles
-          uint32_t b[4];
-          ldmatrix_x4(b[0], b[1], b[2], b[3],
-                      w2_s + ((2 * k + ((lane >> 3) & 1)) * (2 * C) + np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * 16);
-          mma16816(acc[2 * np], a, b[0], b[1]);
-          mma16816(acc[2 * np + 1], a, b[2], b[3]);
-        }
-      }
-#pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        const int p = mt * 16 + g + hrow * 8;
-        const int gy = y0 + p / K::TW, gx = x0 + (p % K::TW);
-        if (gy >= d.H || gx >= d.W) continue;
-        __half *zp = zg + ((size_t)gy * d.W + gx) * C + tig * 2;
-#pragma unroll
-        for (int n = 0; n < NTH; ++n) {
-          const float z0 = acc[n][hrow * 2] * sigmoidf_fast(acc[n + NTH][hrow * 2]);
-          const float z1 = acc[n][hrow * 2 + 1] * sigmoidf_fast(acc[n + NTH][hrow * 2 + 1]);
-          csum[n][0] += z0; csum[n][1] += z1;
-          *reinterpret_cast<uint32_t *>(zp + n * 8) = pack_half2(z0, z1);
-        }
-      }
-    }
-    float *red = reinterpret_cast<float *>(smem + K::S_RED);
-#pragma unroll
-    for (int n = 0; n < NTH; ++n)
-#pragma unroll
-      for (int jx = 0; jx < 2; ++jx) {
-        float v = csum[n][jx];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (g == 0) red[warp * C + n * 8 + tig * 2 + jx] = v;
-      }
-    __syncthreads();
-    if (tid < C) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * C + tid];
-      const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      d.chan_partial[((size_t)t * gridDim.x * gridDim.y + tile_id) * C + tid] = s;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // fold: CALayer2 MLP + beta folded into the per-frame last 1x1
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) cab_fold_kernel(const float *__restrict__ partial, int ntiles, float inv_hw,
@@ -652,57 +317,26 @@ __global__ void __launch_bounds__(256, 3) cab_pass_a2_kernel(const __half *__res
   }
 }
 
-template <int C, bool SHIFT, int TH>
-static int launch_pass_a(const GsnCabPassA &d, cudaStream_t st) {
-  using K = PassACfg<C, SHIFT, TH>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(cab_pass_a_kernel<C, SHIFT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-    attr_set = true;
-  }
-  static const ShiftTable tab = make_shift_table(C);
-  dim3 grid((d.W + K::TW - 1) / K::TW, (d.H + TH - 1) / TH, d.T);
-  cab_pass_a_kernel<C, SHIFT, TH><<<grid, kThreads, K::SMEM, st>>>(d, tab);
-  count_launch();
-  return check_launch("cab_pass_a");
-}
-
-constexpr int kTileH_Cab1 = 16, kTileH_Cab2 = 8;
-
-int cab_pass_a_tc_dispatch(const GsnCabPassA &d, cudaStream_t st);  // cab_pass_a_tc.cu
 int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
 int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b_tc.cu
-
-// GSN_PASS_A_LEGACY=1 selects the mma.sync cross-check implementation of pass A (tests / bisecting only).
-static bool use_legacy_pass_a() {
-  static const bool v = [] { const char *e = getenv("GSN_PASS_A_LEGACY"); return e && e[0] == '1'; }();
-  return v;
-}
 
 }  // namespace gsn
 
 extern "C" int gsn_cab_tiles(int mode, int H, int W) {
-  const int th = !gsn::use_legacy_pass_a() ? 16 : (mode == GSN_MODE_CAB1) ? gsn::kTileH_Cab1 : gsn::kTileH_Cab2;
-  return ((H + th - 1) / th) * ((W + 15) / 16);
+  (void)mode;
+  return ((H + 15) / 16) * ((W + 15) / 16);
 }
 
 extern "C" int gsn_cab_pass_a(const GsnCabPassA *dp, void *stream) {
   using namespace gsn;
   GSN_REQUIRE(dp != nullptr, "cab_pass_a: null descriptor");
   const GsnCabPassA &d = *dp;
-  GSN_REQUIRE(d.x && d.wblob && d.z && d.chan_partial, "cab_pass_a: null pointer");
+  GSN_REQUIRE(d.wblob && d.z && d.chan_partial, "cab_pass_a: null pointer");
+  GSN_REQUIRE(d.a1_pre, "cab_pass_a: a1_pre (the LayerNorm'd planar operand of gsn_ln_planar / gsn_shift_conv1_ln / pass B) is required");
   GSN_REQUIRE(d.T > 0 && d.H > 0 && d.W > 0, "cab_pass_a: empty shape");
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_a: mode=%d", d.mode);
   GSN_REQUIRE(d.debug_stage == 0 || d.debug_out, "cab_pass_a: debug_stage without debug_out");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d.a1_pre) return cab_pass_a_pre_dispatch(d, st);     // LayerNorm'd operand precomputed (gsn_ln_planar)
-  if (!use_legacy_pass_a() || d.mid_ca) return cab_pass_a_tc_dispatch(d, st);
-  if (d.C == 64) {
-    if (d.mode == GSN_MODE_CAB1) return launch_pass_a<64, false, kTileH_Cab1>(d, st);
-    return launch_pass_a<64, true, kTileH_Cab2>(d, st);
-  }
-  set_error("cab_pass_a: C=%d unsupported (64)", d.C);
-  return GSN_E_UNSUPPORTED;
+  return cab_pass_a_pre_dispatch(d, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,
@@ -729,14 +363,12 @@ extern "C" int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float 
   const size_t stride = per_frame_weights ? (size_t)2 * C * C : 0;
   if (C == 64) {
     constexpr int smem = 8 * 129 * 16 + 8 * 128 * 16 + 8 * 64 * 4;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(cab_pass_a2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(cab_pass_a2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cab_pass_a2_kernel<64><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff),
                                                     reinterpret_cast<__half *>(z), chan_partial, hw, stride);
   } else if (C == 80) {
     constexpr int smem = 10 * 129 * 16 + 10 * 160 * 16 + 8 * 80 * 4;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(cab_pass_a2_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(cab_pass_a2_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cab_pass_a2_kernel<80><<<grid, 256, smem, st>>>(reinterpret_cast<const __half *>(u), reinterpret_cast<const __half *>(w2eff),
                                                     reinterpret_cast<__half *>(z), chan_partial, hw, stride);
   } else {
@@ -775,13 +407,11 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   dim3 grid((unsigned)((hw + 127) / 128), d.T);
   if (d.C == 64) {
     constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(cab_pass_b_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cab_pass_b_kernel<64><<<grid, 256, smem, st>>>(d);
   } else if (d.C == 80) {
     constexpr int smem = 2 * 10 * 129 * 16 + 10 * 80 * 16;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(cab_pass_b_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(cab_pass_b_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cab_pass_b_kernel<80><<<grid, 256, smem, st>>>(d);
   } else {
     set_error("cab_pass_b: C=%d unsupported (64, 80)", d.C);

@@ -2,7 +2,8 @@
 
 Weights follow nn.Conv2d's default-init distribution, but every ``beta`` (zero-initialised in
 the reference, gshift_deblur2.py:208,243 -- which would switch every CAB1/CAB2 branch off),
-LayerNorm affine and PReLU slope is randomised so the fused kernels are actually exercised.
+LayerNorm affine and PReLU slope is randomised, and the channel-attention logits are given a realistic
+spread (non-uniform per-channel scales), so the fused kernels and every fold are actually exercised.
 CPU generator => identical values in the build container and on the GPU box.
 """
 import math
@@ -24,6 +25,11 @@ def randomize_(net: torch.nn.Module, seed: int = 1234) -> None:
                 p.copy_(0.25 + 0.05 * torch.randn(p.shape, generator=g))
             elif p.dim() == 4:                                         # conv weight
                 bound = 1.0 / math.sqrt(p.shape[1] * p.shape[2] * p.shape[3])
+                if ".conv_du.2." in name:
+                    # channel attention (CALayer / CALayer2, gshift_deblur2.py:54-89): with default-init weights every
+                    # sigmoid sits within 0.02 of 0.5, so a scale applied to the wrong channel or the wrong side of a
+                    # conv would be invisible to the parity tests; x20 spreads the per-channel scales over ~0.05..0.95
+                    bound *= 20.0
                 p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
             else:                                                      # conv bias
                 p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * 0.1)

@@ -1,0 +1,293 @@
+"""GPU parity, part 2 (-m gpu):
+
+* BIT-EXACT tests of the integer/index part of the path -- the grouped spatial shift gather and the half-channel temporal roll
+  (gshift_deblur2.py:465-519) -- through the kernels that carry them (gsn_shift_conv1 with a delta conv1, pass B with a zero
+  weight, gsn_roll_copy), against the oracle's index maps (which tests/test_oracle_cpu.py pins to the reference by sha256);
+* scale-placement tests with NON-UNIFORM channel-attention scales (grouped RepConv of Ours+ denoise);
+* the whole net against the oracle at the sizes bench.py measures: BASELINE configs K2 (Ours-s 720p T=20), K3 (Ours+ 720p T=52),
+  one K4 tile (denoise, 68 x 272 x 448) and a K5-shaped Ours+ 1080p clip.  The checker there is the oracle run in fp32 on the GPU
+  (TF32 off), itself pinned to the CPU oracle at K1 in this file.  Contract: PSNR(ours, oracle fp32)
+  >= 60 dB on [0,1] outputs and |PSNR(ours,gt) - PSNR(oracle,gt)| / PSNR(oracle,gt) <= 1e-3.
+"""
+import ctypes as C
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_io as gio
+
+sys.path.insert(0, os.path.join(gio.ROOT, "oracle"))
+import shiftnet_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda:0"
+L = gio.pkg("host.lib")
+P = gio.pkg("host.packing")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def nhwc16(x):
+    """(T,C,H,W) fp32 cpu -> (T,H,W,C) fp16 cuda (C % 8 == 0 here)."""
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV).half()
+
+
+def int_valued(T, Cc, H, W, seed):
+    """fp16-exact, all-distinct-ish values: small integers / 8 (any index mix-up changes the result)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-1024, 1024, (T, Cc, H, W), generator=g).float() / 8.0
+
+
+# ------------------------------------------------------------------------------------------------ exact index maps
+@pytest.mark.parametrize("Cc", [64, 80])
+@pytest.mark.parametrize("circular", [True, False])
+@pytest.mark.parametrize("shape", [(1, 12, 20), (2, 9, 33), (5, 37, 50)])
+def test_shift_gather_index_map_bit_exact(Cc, circular, shape):
+    """gsn_shift_conv1 with conv1 = delta (centre tap 1, others 0) must return spatial_shift2(neighbour half) EXACTLY:
+    24 offsets, zero fill, the circular / clamped neighbour frame (gshift_deblur2.py:465-519, gshift_deblur1.py:504-528)."""
+    lib = L.load()
+    T, H, W = shape
+    x = int_valued(T, Cc, H, W, 100 + Cc + T)
+    xd = nhwc16(x)
+    wc1 = torch.zeros(9, Cc // 2, dtype=torch.float16, device=DEV)
+    wc1[4] = 1.0
+    for rev in (False, True):
+        out = torch.empty(T, H, W, Cc // 2, dtype=torch.float16, device=DEV)
+        L.check(lib.gsn_shift_conv1(xd.data_ptr(), T, H, W, Cc, L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, int(circular),
+                                    wc1.data_ptr(), out.data_ptr(), _stream()), "shift_conv1")
+        torch.cuda.synchronize()
+        _, hw = O.temporal_roll(x, rev, circular)
+        ref = O.spatial_shift(hw, Cc)
+        got = out.permute(0, 3, 1, 2).float().cpu()
+        assert torch.equal(got, ref), f"C={Cc} rev={rev} circular={circular} {shape}: {(got != ref).sum().item()} elements differ"
+
+
+@pytest.mark.parametrize("Cc", [64, 80])
+@pytest.mark.parametrize("circular", [True, False])
+def test_temporal_roll_shortcut_bit_exact(Cc, circular):
+    """Pass B with a zero effective weight returns its shortcut: the rolled stream for the CAB2 modes (gshift_deblur2.py:253,257),
+    x itself for CAB1 -- bit-exact against the oracle's temporal_roll, C=64 (tcgen05 streaming kernel) and C=80."""
+    lib = L.load()
+    for T, H, W in ((1, 8, 16), (2, 9, 33), (5, 40, 52)):
+        x = int_valued(T, Cc, H, W, 7 + T)
+        xd = nhwc16(x)
+        z = torch.randn(T, H, W, Cc, device=DEV).half()
+        weff = torch.zeros(T, Cc * Cc, dtype=torch.float16, device=DEV)
+        beff = torch.zeros(T, Cc, dtype=torch.float32, device=DEV)
+        for mode, rev in ((L.MODE_CAB2_FWD, False), (L.MODE_CAB2_REV, True), (L.MODE_CAB1, None)):
+            out = torch.empty(T, H, W, Cc, dtype=torch.float16, device=DEV)
+            b = L.CabPassB()
+            b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, int(circular)
+            b.x, b.z, b.weff, b.beff, b.out = xd.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
+            L.check(lib.gsn_cab_pass_b(C.byref(b), _stream()), "cab_pass_b")
+            torch.cuda.synchronize()
+            ref = x if rev is None else O.temporal_roll(x, rev, circular)[0]
+            got = out.permute(0, 3, 1, 2).float().cpu()
+            assert torch.equal(got, ref), f"C={Cc} mode={mode} circular={circular} T={T}: {(got != ref).sum().item()} differ"
+
+
+def test_roll_copy_bit_exact():
+    """Shift_CAB.channel_shift of Ours+ denoise (gshift_denoise1.py:167-179): clamped roll, real channels 24 of 24 / 80 of 80."""
+    lib = L.load()
+    for Cc, T, H, W in ((24, 3, 10, 12), (80, 4, 9, 16), (24, 1, 6, 8)):
+        x = int_valued(T, Cc, H, W, Cc + T)
+        xd = nhwc16(x)
+        for rev in (False, True):
+            y = torch.empty_like(xd)
+            L.check(lib.gsn_roll_copy(xd.data_ptr(), y.data_ptr(), T, H, W, Cc, Cc, int(rev), _stream()), "roll_copy")
+            torch.cuda.synchronize()
+            assert torch.equal(y.permute(0, 3, 1, 2).float().cpu(), O.temporal_roll(x, rev, False)[0])
+
+
+# ------------------------------------------------------------------------------------------------ scale placement
+def test_group_conv5_nonuniform_scale():
+    """gsn_group_conv5 with a per-channel scale spanning 0.05..0.95 must equal RepConv(s * g) (gshift_denoise1.py:190-191,
+    224-225): conv5x5(s g) + conv3x3(s g) + s g with groups of 8 -- the scale sits on the INPUT of the grouped conv."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(21)
+    T, Cc, H, W = 2, 80, 37, 45
+    x = torch.randn(T, Cc, H, W, generator=g)
+    w5 = torch.randn(Cc, 8, 5, 5, generator=g) / 200 ** 0.5
+    w3 = torch.randn(Cc, 8, 3, 3, generator=g) / 72 ** 0.5
+    s = 0.05 + 0.9 * torch.rand(T, Cc, generator=g)
+    wfrag = P.pack_group_conv5(w5, w3).to(DEV)
+    xd = nhwc16(x)
+    sd_ = s.to(DEV).contiguous()
+    for scale in (None, sd_):
+        out = torch.empty(T, H, W, Cc, dtype=torch.float16, device=DEV)
+        L.check(lib.gsn_group_conv5(xd.data_ptr(), T, H, W, Cc, wfrag.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                    out.data_ptr(), _stream()), "group_conv5")
+        torch.cuda.synchronize()
+        xin = x.half().float()
+        if scale is not None:
+            xin = (xin * s.view(T, Cc, 1, 1)).half().float()          # the kernel rounds the scaled tile to fp16
+        wm = w5.clone()
+        wm[:, :, 1:4, 1:4] += w3                                        # host/packing.py merges the two tap sets in fp32 -> fp16
+        wm = wm.half().float()
+        ref = F.conv2d(xin, wm, None, padding=2, groups=Cc // 8) + xin
+        got = out.permute(0, 3, 1, 2).float().cpu()
+        r = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        print(f"[parity] group_conv5 scale={'yes' if scale is not None else 'no'}: rel_rms={r:.2e}")
+        assert r < 1.5e-3
+        if scale is not None:     # and the old (wrong) placement must be distinguishable at this tolerance
+            wrong = (F.conv2d(x.half().float(), wm, None, padding=2, groups=Cc // 8) + x.half().float()) * s.view(T, Cc, 1, 1)
+            assert ((wrong - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() > 0.05
+
+
+def test_conv_in_noise_map_strided_vs_cat():
+    """gsn_conv_in_nm reads the noise map through its strides (expand()ed (1,T,1,H,W) view of one scalar, as
+    inference/test_denoise_small.py:162 passes it) -- same result as the conv over torch.cat((x, noise_map), 1)."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(3)
+    T, H, W = 3, 20, 36
+    x = torch.rand(T, 3, H, W, generator=g)
+    w = torch.randn(14, 4, 3, 3, generator=g) / 6.0
+    b = torch.randn(14, generator=g) * 0.1
+    wi, bi = P.pack_conv_in(w, b, 16)
+    wi, bi = wi.to(DEV), bi.to(DEV)
+    for tdt, dt in ((torch.float16, L.DTYPE_F16), (torch.float32, L.DTYPE_F32)):
+        xd = x.to(DEV, tdt).contiguous()
+        std = torch.full((1, 1, 1, 1, 1), 30.0 / 255, device=DEV, dtype=tdt)
+        dense = (torch.rand(1, T, 1, H, W, generator=g) * 0.2).to(DEV, tdt)
+        for nm5 in (std.expand(1, T, 1, H, W), dense):
+            nm = nm5[0]
+            st = nm.stride()
+            f0 = torch.empty(T, H, W, 16, dtype=torch.float16, device=DEV)
+            L.check(lib.gsn_conv_in_nm(xd.data_ptr(), dt, T, 3, H, W, nm.data_ptr(), st[0], st[2], st[3], wi.data_ptr(), bi.data_ptr(),
+                                       16, f0.data_ptr(), _stream()), "conv_in_nm")
+            torch.cuda.synchronize()
+            ref = F.conv2d(torch.cat((xd, nm.expand(T, 1, H, W)), 1).float().cpu(), w, b, padding=1)
+            got = f0[..., :14].permute(0, 3, 1, 2).float().cpu()
+            r = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+            assert r < 1.5e-3, r
+            assert f0[..., 14:].abs().max().item() == 0.0
+
+
+def test_plus_archs_reject_sizes_not_multiple_of_8():
+    """Ours+ halves the resolution three times in stage 1: H % 8 == 4 makes the reference raise in SkipUpSample
+    (gshift_deblur1.py:352); the engine raises too instead of reading a mismatched skip tensor."""
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur1")
+    net = importlib.import_module("basicsr.models.archs.gshift_deblur1").GShiftNet(future_frames=2, past_frames=2)
+    net.load_state_dict(sd)
+    net = net.half().to(DEV).eval()
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 6, 3, 36, 40, device=DEV).half())
+    out = net(torch.rand(1, 6, 3, 40, 48, device=DEV).half())
+    assert tuple(out.shape) == (2, 3, 40, 48)
+
+
+# ------------------------------------------------------------------------------------------------ parity at benchmark sizes
+def cuda_oracle(sd, spec, x, nm=None):
+    """The oracle (oracle/shiftnet_oracle.py is device-agnostic torch code) in fp32 on the GPU, TF32 off."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sdd = {k: v.to(DEV, torch.float32) for k, v in sd.items()}
+        out = O.gshiftnet_forward(sdd, O.ARCHS[spec.name], x.to(DEV, torch.float32), None if nm is None else nm.to(DEV, torch.float32))
+        torch.cuda.synchronize()
+        return out.cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
+def _ours(sd, spec, x, nm=None):
+    net = importlib.import_module("basicsr.models.archs." + spec.name).GShiftNet(future_frames=2, past_frames=2)
+    net.load_state_dict(sd)
+    net = net.half().to(DEV).eval()
+    out = net(x.to(DEV).half(), nm.to(DEV).half()) if spec.denoise else net(x.to(DEV).half())
+    out = out.float().cpu()
+    del net
+    torch.cuda.empty_cache()
+    return out
+
+
+def _contract(out, ref, gt, x, what):
+    """>= 60 dB against the fp32 oracle, relative PSNR-vs-GT drift <= 1e-3.  Also reported (and bounded):
+    the error relative to what the network actually computes, ||out - ref|| / ||ref - x||."""
+    p = O.psnr(out, ref)
+    gtc = gt[0, 2:-2]
+    pg_ref, pg_out = O.psnr(ref.clamp(0, 1), gtc), O.psnr(out.clamp(0, 1), gtc)
+    drift = abs(pg_out - pg_ref) / pg_ref
+    resid = ((out - ref).pow(2).mean().sqrt() / (ref - x[0, 2:-2, :3]).pow(2).mean().sqrt()).item()
+    print(f"[parity-at-size] {what}: PSNR(cuda, oracle fp32) = {p:.2f} dB ; PSNR-vs-GT oracle {pg_ref:.4f} ours {pg_out:.4f} "
+          f"drift {drift:.2e} ; error / net residual = {resid:.2e} ; max|diff| = {(out - ref).abs().max().item():.2e}")
+    assert torch.isfinite(out).all()
+    assert p >= 60.0 and drift <= 1e-3 and resid <= 5e-3, (what, p, drift, resid)
+
+
+def test_cuda_oracle_pinned_to_cpu_oracle_at_k1():
+    """The checker of the size tests: the same oracle code in fp32 on the GPU against the CPU oracle on BASELINE config K1."""
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
+    gt, x = gio.pkg("host.synth").synthetic_clip(8, 256, 256)
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(min(16, os.cpu_count() or 1))      # the many small convs oversubscribe a 128-thread host badly
+    try:
+        cpu = O.gshiftnet_forward(sd, O.ARCHS[spec.name], x)
+    finally:
+        torch.set_num_threads(nthr)
+    gpu = cuda_oracle(sd, spec, x)
+    p = O.psnr(gpu, cpu)
+    print(f"[parity-at-size] oracle fp32 on CUDA vs on CPU at K1: {p:.2f} dB, max|diff| {(gpu - cpu).abs().max().item():.2e}")
+    assert p >= 100.0
+    _contract(_ours(sd, spec, x), cpu, gt, x, "K1 Ours-s 256x256 T=8 (vs CPU oracle)")
+
+
+SIZE_CASES = [
+    # name, arch, T, H, W
+    ("K2_ours_s_720p_T20", "gshift_deblur2", 20, 720, 1280),
+    ("K3_ours_plus_720p_T52", "gshift_deblur1", 52, 720, 1280),
+    ("K4tile_denoise_s_272x448_T68", "gshift_denoise2", 68, 272, 448),
+    ("K4tile_denoise_plus_272x448_T20", "gshift_denoise1", 20, 272, 448),
+    ("K5shape_ours_plus_1080p_T12", "gshift_deblur1", 12, 1080, 1920),
+]
+
+
+@pytest.mark.parametrize("case", SIZE_CASES, ids=[c[0] for c in SIZE_CASES])
+def test_full_forward_at_benchmark_size_vs_oracle(case):
+    name, arch, T, H, W = case
+    sd, spec = gio.synthetic_checkpoint(arch)
+    synth = gio.pkg("host.synth")
+    if spec.denoise:
+        gt, x, nm = synth.synthetic_clip(T, H, W, denoise_sigma=30)
+    else:
+        (gt, x), nm = synth.synthetic_clip(T, H, W), None
+    out = _ours(sd, spec, x, nm)
+    ref = cuda_oracle(sd, spec, x, nm)
+    _contract(out, ref, gt, x, name)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU entry point
+def test_inference_entry_point_two_ranks_nccl(tmp_path):
+    """inference/test_deblur_small.py under torchrun on 2 GPUs: units shard across ranks, ONE NCCL all_gather of the
+    (video, frame, psnr, ssim) records, rank 0 prints the same totals as a single-rank run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(gio.ROOT, "inference", "test_deblur_small.py")
+    common = ["--synthetic", "3", "--one_len", "4", "--synthetic_frames", "12"]
+    env = dict(os.environ, NCCL_DEBUG="WARN")
+    one = subprocess.run([sys.executable, script] + common + ["--result_path", str(tmp_path / "n1")],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", script] + common + ["--result_path", str(tmp_path / "n2")],
+                         capture_output=True, text=True, timeout=900, env=env)
+    assert two.returncode == 0, two.stderr[-3000:]
+    l1 = [l for l in one.stdout.splitlines() if l.startswith("# ")]
+    l2 = [l for l in two.stdout.splitlines() if l.startswith("# ")]
+    assert l1 == l2 and l1[-1].startswith("# Total AVG-PSNR="), (l1, l2)
+    ranks = {l.split("]")[0] for l in two.stdout.splitlines() if l.startswith("> [rank ")}
+    assert ranks == {"> [rank 0", "> [rank 1"}, ranks
+    out_dir = os.path.join(gio.ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "infer_two_ranks.log"), "w") as f:
+            f.write(two.stdout + "\n--- stderr ---\n" + two.stderr[-4000:])
