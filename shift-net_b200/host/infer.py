@@ -93,6 +93,11 @@ def plan_units(videos, task, one_len):
     return units
 
 
+def frame_bases(units):
+    """{(video, kk): index of the chunk's first output frame within its video} -- the reference's running `index`."""
+    return {(v, kk): sum(len(u[2]) - 4 for u in units if u[0] == v and u[1] < kk) for v, kk, _, _ in units}
+
+
 def load_frames(frames):
     """paths / arrays -> list of uint8 HWC arrays cropped to multiples of 4 (test_deblur_small.py:122-127)."""
     frames = [np.asarray(_imread(f) if isinstance(f, str) else f) for f in frames]
@@ -212,10 +217,13 @@ def run(net_cls, task, args):
     if args.model_path and os.path.exists(args.model_path):
         net.load_state_dict(torch.load(args.model_path, map_location="cpu")["params"])
         log.write_log("Loading model from {}".format(args.model_path))
-    else:
+    elif args.synthetic or getattr(args, "random_weights", False):
         importlib_synth = __import__("importlib").import_module("shift-net_b200.host.synth")
         importlib_synth.randomize_(net, 1234)
-        log.write_log("No checkpoint at {!r}: using the seeded synthetic checkpoint".format(args.model_path))
+        log.write_log("No checkpoint at {!r}: using the seeded synthetic checkpoint (--synthetic / --random_weights)".format(args.model_path))
+    else:
+        # the reference fails hard in torch.load (test_deblur_small.py:85); metrics of random weights would look plausible
+        raise FileNotFoundError("checkpoint {!r} not found (pass --synthetic N or --random_weights to run without one)".format(args.model_path))
     net = net.half().to(device).eval()
 
     if args.synthetic:
@@ -228,6 +236,9 @@ def run(net_cls, task, args):
     names = sorted(videos)
     units = plan_units(videos, task, getattr(args, "one_len", 0))
     records = []
+    # running frame index per video, as the reference keeps it (test_denoise_small.py:184-189): the last denoise chunk is longer
+    # than the others, so kk * chunk_len would mis-number its frames
+    frame_base = frame_bases(units)
     dio = DeviceIO(device) if (use_cuda and not getattr(args, "cpu_io", False)) else None
     with torch.no_grad():
         for ui in range(rank, len(units), world):             # clip sharding: unit i -> rank i % world
@@ -266,7 +277,7 @@ def run(net_cls, task, args):
                 o = net(x[..., H // 2 - ph:, W // 2 - pw:].contiguous(), nm).float(); out[..., H // 2:, W // 2:] = o[..., ph:, pw:]
             t1 = time.time()
             imgs = (out.clamp(0, 1.0) * 255).permute(0, 2, 3, 1).cpu().numpy()
-            base = kk * (T - 4)
+            base = frame_base[(v, kk)]
             for e in range(imgs.shape[0]):
                 p = gpu_psnr[e] if gpu_psnr is not None else psnr_255(imgs[e], gts[e])
                 s = ssim_calculate(imgs[e], gts[e])
@@ -292,6 +303,7 @@ def add_common_args(parser):
     parser.add_argument("--model_path", type=str, default=None)
     parser.add_argument("--result_path", type=str, default=None)
     parser.add_argument("--cpu_io", action="store_true", help="reference-style host I/O: float conversion and PSNR on the CPU")
+    parser.add_argument("--random_weights", action="store_true", help="run without a checkpoint on the seeded synthetic weights")
     parser.add_argument("--synthetic", type=int, default=0, help="number of synthetic videos (no dataset needed)")
     parser.add_argument("--synthetic_frames", type=int, default=12)
     parser.add_argument("--synthetic_h", type=int, default=64)

@@ -100,3 +100,15 @@ def test_to_tensor_matches_reference_numpy2tensor_arithmetic():
     # the CUDA kernel (gsn_u8_to_clip) computes float32(u8) * float32(1/255) with one rounding: the same values
     k = np.float32(1.0 / 255.0)
     assert np.array_equal((np.arange(256, dtype=np.float32) * k), ref[0].reshape(-1).numpy())
+
+
+def test_denoise_chunking_numbers_frames_with_a_running_index():
+    """test_denoise_small.py:113-131,184-189: 107 frames -> one_len 51, chunks of 51 and 52 (the last takes the remainder); the
+    second chunk's frames start at 51, not at kk * its own length."""
+    infer = gio.pkg("host.infer")
+    videos = {"a": (list(range(107)), list(range(107))), "b": (list(range(20)), list(range(20)))}
+    units = infer.plan_units(videos, "denoise", 0)
+    assert [(u[0], u[1], len(u[2]) - 4) for u in units] == [("a", 0, 51), ("a", 1, 52), ("b", 0, 16)]
+    assert infer.frame_bases(units) == {("a", 0): 0, ("a", 1): 51, ("b", 0): 0}
+    units = infer.plan_units({"c": (list(range(40)), list(range(40)))}, "deblur", 8)
+    assert infer.frame_bases(units) == {("c", k): 8 * k for k in range(4)}
