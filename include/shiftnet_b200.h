@@ -150,6 +150,8 @@ int gsn_add(const void *a, const void *b, void *out, long long n, void *stream);
 #define GSN_MODE_CAB1 0
 #define GSN_MODE_CAB2_FWD 1
 #define GSN_MODE_CAB2_REV 2
+/* GsnCabPassA.debug_stage value that routes the call to the row-streaming pass-A kernel whatever GSN_PASS_A_STREAM says */
+#define GSN_PASS_A_FORCE_STREAM 100
 
 typedef struct {
   int T, H, W, C;       /* C = 64 (Ours-s); activations (T,H,W,C) NHWC fp16 */
@@ -174,6 +176,9 @@ typedef struct {
 } GsnCabPassA;
 
 int gsn_cab_tiles(int mode, int H, int W);
+/* Number of per-frame partial-sum slots gsn_cab_pass_a writes for this problem: chan_partial is [T][slots][C]; slots depend on
+ * which pass-A kernel serves the call (row-streaming pieces for C = 64 without mid_ca, 16x16 tiles otherwise). */
+int gsn_cab_pass_a_tiles(int T, int H, int W, int C, int mid_ca, int debug_stage);
 int gsn_cab_pass_a(const GsnCabPassA *d, void *stream);
 
 /* LayerNorm2d of CAB1 / CAB2 (d2:19-28,44-53,209,250) as its own HBM-bound kernel, for GsnCabPassA.a1_pre:

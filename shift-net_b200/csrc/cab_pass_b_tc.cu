@@ -48,10 +48,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr_bytes) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-
 __global__ void __launch_bounds__(kPbThreads, 1) cab_pass_b_tc_kernel(const GsnCabPassB d, const __grid_constant__ CUtensorMap tm_z,
                                                                       const __grid_constant__ CUtensorMap tm_x,
                                                                       const __grid_constant__ CUtensorMap tm_out) {

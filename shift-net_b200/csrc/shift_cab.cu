@@ -318,7 +318,18 @@ __global__ void __launch_bounds__(256, 3) cab_pass_a2_kernel(const __half *__res
 }
 
 int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
-int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b_tc.cu
+int cab_pass_a_stream_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_stream.cu
+bool pass_a_stream_enabled();
+int pass_a_stream_tiles(int T, int H, int W);
+// Two pass-A kernels serve C = 64: the 16x16-tile kernel (cab_pass_a_pre.cu, default) and the row-streaming warp-specialised
+// kernel (cab_pass_a_stream.cu; deblur nets only: no mid channel attention).  They measure the same on B200,
+// the tile kernel moves fewer DRAM bytes, so it stays the default; GSN_PASS_A_STREAM=1 (process-wide) or
+// debug_stage == GSN_PASS_A_FORCE_STREAM (per call, tests) select the streaming kernel.
+static bool use_stream(int C, int mid_ca, int debug_stage) {
+  if (C != 64 || mid_ca) return false;
+  if (debug_stage == GSN_PASS_A_FORCE_STREAM) return true;
+  return pass_a_stream_enabled() && !debug_stage;
+}
 
 }  // namespace gsn
 
@@ -336,7 +347,13 @@ extern "C" int gsn_cab_pass_a(const GsnCabPassA *dp, void *stream) {
   GSN_REQUIRE(d.T > 0 && d.H > 0 && d.W > 0, "cab_pass_a: empty shape");
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_a: mode=%d", d.mode);
   GSN_REQUIRE(d.debug_stage == 0 || d.debug_out, "cab_pass_a: debug_stage without debug_out");
+  if (use_stream(d.C, d.mid_ca, d.debug_stage)) return cab_pass_a_stream_dispatch(d, reinterpret_cast<cudaStream_t>(stream));
   return cab_pass_a_pre_dispatch(d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gsn_cab_pass_a_tiles(int T, int H, int W, int C, int mid_ca, int debug_stage) {
+  if (gsn::use_stream(C, mid_ca, debug_stage)) return gsn::pass_a_stream_tiles(T, H, W);
+  return ((H + 15) / 16) * ((W + 15) / 16);
 }
 
 extern "C" int gsn_cab_fold_mid(const float *partial, int ntiles, float inv_hw, const float *w_du0, const float *w_du2, int cr,

@@ -35,6 +35,7 @@ class Engine:
         # CAB1's by the epilogue of the preceding pass B (GsnCabPassB.a1_next).  GSN_LN_FUSE=0 runs the un-fused chain
         # gsn_shift_conv1 -> gsn_ln_planar instead (cross-check in the tests).
         self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
+        self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
         self._a1_next = None
         # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
         self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"
@@ -355,7 +356,10 @@ class Engine:
         if ck not in self.cache:
             self.cache[ck] = self._up((P.pack_cab_pass_a(self.sd, p, Cc, shift, self.boff), P.pack_cab_fold(self.sd, p, self.boff)))
         blob, fw = self.cache[ck]
-        ntiles = self.lib.gsn_cab_tiles(mode, H, W)
+        # pass-A kernel choice (C-ABI: GsnCabPassA.debug_stage): 0 = library default (16x16-tile kernel unless GSN_PASS_A_STREAM=1),
+        # PASS_A_FORCE_STREAM = the row-streaming kernel for this call (deblur nets; tests and A/B measurements)
+        stage_sel = debug_stage or (L.PASS_A_FORCE_STREAM if (self.pass_a_stream and not self.spec.denoise) else 0)
+        ntiles = self.lib.gsn_cab_pass_a_tiles(T, H, W, Cc, 1 if self.spec.denoise else 0, stage_sel)
         z = self._new(T, H, W, Cc)
         partial = self._new(T, ntiles, Cc, dtype=torch.float32)
         a = L.CabPassA()
@@ -389,6 +393,8 @@ class Engine:
         if debug_stage:
             dbg = torch.zeros(T * ntiles * 12 * 512 * 8, dtype=torch.float16, device=self.dev)
             a.debug_stage, a.debug_out = debug_stage, dbg.data_ptr()
+        elif stage_sel:
+            a.debug_stage, a.debug_out = stage_sel, z.data_ptr()       # no dump is written; the field only selects the kernel
         with self._timed(("cab_pass_a_shift" if shift else "cab_pass_a") + (f"[{H}x{W}]" if self.timeline_detail else ""), T * H * W):
             L.check(self.lib.gsn_cab_pass_a(C.byref(a), self._stream()), "cab_pass_a " + p)
         if self.spec.denoise:

@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libshiftnet_b200.so")
 EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in", "gsn_conv_in_nm",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
-    "gsn_cab_pass_a", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
+    "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
     "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
     "gsn_cab_dense_tiles", "gsn_cab_dense", "gsn_u8_to_clip", "gsn_psnr_sse_blocks", "gsn_psnr_sse",
 ]
 
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
 DTYPE_F16, DTYPE_F32 = 0, 1
+PASS_A_FORCE_STREAM = 100      # GsnCabPassA.debug_stage: GSN_PASS_A_FORCE_STREAM
 
 
 class ConvDesc(C.Structure):
@@ -85,6 +86,7 @@ def load():
     lib.gsn_upsample2x_add.argtypes = [vp, vp, vp, i, i, i, i, vp]
     lib.gsn_add.argtypes = [vp, vp, vp, ll, vp]
     lib.gsn_cab_tiles.argtypes = [i, i, i]
+    lib.gsn_cab_pass_a_tiles.argtypes = [i, i, i, i, i, i]
     lib.gsn_cab_pass_a.argtypes = [C.POINTER(CabPassA), vp]
     lib.gsn_cab_fold.argtypes = [vp, i, f, vp, vp, i, vp, vp, vp, i, i, vp, vp, vp]
     lib.gsn_cab_pass_b.argtypes = [C.POINTER(CabPassB), vp]
