@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(256, 3) cab_pass_a2_kernel(const __half *__res
 
 int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
 int cab_pass_a_stream_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_stream.cu
+int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b_tc.cu
 bool pass_a_stream_enabled();
 int pass_a_stream_tiles(int T, int H, int W);
 // Two pass-A kernels serve C = 64: the 16x16-tile kernel (cab_pass_a_pre.cu, default) and the row-streaming warp-specialised
