@@ -124,6 +124,14 @@ int gsn_u8_to_clip(const void *frames_u8, int T, int H, int W, int dtype, void *
 int gsn_psnr_sse_blocks(void);
 int gsn_psnr_sse(const void *out, int dtype, const void *gt_u8, int T, int H, int W, double *partial, void *stream);
 
+/* SSIM of the same loop (inference/test_deblur_small.py:25-49) on the device: scipy's 3-D gaussian_filter(sigma=1.5) semantics
+ * (13 taps along the channel, H and W axes, 'reflect' boundary, float64 accumulation and float32 rounding per axis pass).
+ * partial[t][b] (b < gsn_ssim_blocks()) = float64 partial sums of the SSIM map of frame t; SSIM = sum / (3 H W).
+ * workspace: gsn_ssim_workspace_bytes(T,H,W) bytes of device memory. */
+int gsn_ssim_blocks(void);
+long long gsn_ssim_workspace_bytes(int T, int H, int W);
+int gsn_ssim(const void *out, int dtype, const void *gt_u8, int T, int H, int W, void *workspace, double *partial, void *stream);
+
 /* CALayer squeeze-excite MLP (d2:54-71): s[t][c] = sigmoid(W2 relu(W1 mean_hw)), from per-tile sums.
  * partial [T][ntiles][cp]; w1 fp32 [cr][c]; w2 fp32 [c][cr]; s fp32 [T][cp]. */
 int gsn_ca_scale(const float *partial, int ntiles, float inv_hw, const float *w1, const float *w2, int c, int cr, int cp,

@@ -125,6 +125,7 @@ class DeviceIO:
         self.lib = self.L.load()
         self.dev = device
         self.nb = self.lib.gsn_psnr_sse_blocks()
+        self.nbs = self.lib.gsn_ssim_blocks()
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -155,6 +156,23 @@ class DeviceIO:
                 sse += v
             mse = sse / (3.0 * H * W)
             res.append(float("inf") if mse == 0 else 10.0 * math.log10(255.0 ** 2 / mse))
+        return res
+
+    def ssim(self, out, gt_dev):
+        """out (T,3,H,W) fp16/fp32 as returned by the net, gt_dev (T,H,W,3) uint8 -> list of T SSIM values: the reference's
+        ssim_calculate (scipy 3-D Gaussian, sigma 1.5) on the device (gsn_ssim); 128 doubles per frame come back."""
+        T, _, H, W = out.shape
+        out = out.contiguous()
+        ws = torch.empty(self.lib.gsn_ssim_workspace_bytes(T, H, W), dtype=torch.uint8, device=self.dev)
+        part = torch.empty(T, self.nbs, dtype=torch.float64, device=self.dev)
+        dt = self.L.DTYPE_F16 if out.dtype == torch.float16 else self.L.DTYPE_F32
+        self.L.check(self.lib.gsn_ssim(out.data_ptr(), dt, gt_dev.data_ptr(), T, H, W, ws.data_ptr(), part.data_ptr(), self._stream()), "ssim")
+        res = []
+        for row in part.cpu().tolist():
+            s = 0.0
+            for v in row:                     # fixed order: deterministic
+                s += v
+            res.append(s / (3.0 * H * W))
         return res
 
 
@@ -244,43 +262,56 @@ def run(net_cls, task, args):
         for ui in range(rank, len(units), world):             # clip sharding: unit i -> rank i % world
             v, kk, in_seq, gt_seq = units[ui]
             t0 = time.time()
-            gpu_psnr = None
+            gpu_psnr = gpu_ssim = None
             if task == "deblur" and dio is not None:
-                # device I/O path: uint8 H2D, /255 and the PSNR reduction on the GPU (SSIM stays on the host as in the reference)
+                # device I/O path: uint8 H2D, /255, PSNR and SSIM reductions on the GPU -- only scalars come back over PCIe
                 ins, gts = load_frames(in_seq), load_frames(gt_seq)
                 x = dio.clip_from_u8(dio.upload_u8(ins))
-                T = x.shape[1]
                 out = net(x)
-                gpu_psnr = dio.psnr(out, dio.upload_u8(gts))
-                out = out.float()
+                gt_dev = dio.upload_u8(gts)
+                gpu_psnr, gpu_ssim = dio.psnr(out, gt_dev), dio.ssim(out, gt_dev)
             elif task == "deblur":
                 x, _ = to_tensor(in_seq)
                 _, gts = to_tensor(gt_seq)
-                T = x.shape[1]
                 out = net(x.to(device).half()).float()
             else:
-                x, _ = to_tensor(in_seq)
-                _, gts = to_tensor(gt_seq)
-                T = x.shape[1]
                 sigma = args.sigma / 255.0
-                g = torch.Generator().manual_seed(1000 * names.index(v) + kk)
-                x = (x + sigma * torch.randn(x.shape, generator=g)).to(device).half()
+                gts = load_frames(gt_seq)
+                if dio is not None:
+                    # clean frames travel as uint8; the AWGN is drawn on the host with the per-unit seed (as --cpu_io does) or, with
+                    # --device_noise, on the GPU (same distribution, different stream: no float clip crosses PCIe at all)
+                    x = dio.clip_from_u8(dio.upload_u8(load_frames(in_seq)), torch.float32)
+                    if getattr(args, "device_noise", False):
+                        gd = torch.Generator(device=device).manual_seed(1000 * names.index(v) + kk)
+                        x = (x + sigma * torch.randn(x.shape, generator=gd, device=device)).half()
+                    else:
+                        g = torch.Generator().manual_seed(1000 * names.index(v) + kk)
+                        x = (x + (sigma * torch.randn(x.shape, generator=g)).pin_memory().to(device, non_blocking=True)).half()
+                else:
+                    x, _ = to_tensor(in_seq)
+                    g = torch.Generator().manual_seed(1000 * names.index(v) + kk)
+                    x = (x + sigma * torch.randn(x.shape, generator=g)).to(device).half()
                 B, N, _, H, W = x.shape
                 std = torch.full((1, 1, 1, 1, 1), sigma, device=device, dtype=torch.float16)
                 ph, pw = 32 - (H // 2 % 16), 32 - (W // 2 % 16)   # 2x2 overlapped tiling, test_denoise_small.py:153-173
                 out = torch.zeros(N - 4, 3, H, W, device=device)
                 hh, ww = H // 2 + ph, W // 2 + pw
-                nm = std.expand(B, N, 1, hh, ww)
+                nm = std.expand(B, N, 1, hh, ww)                  # the four tiles share one shape: one CUDA graph serves them all
                 o = net(x[..., 0:hh, 0:ww].contiguous(), nm).float(); out[..., 0:H // 2, 0:W // 2] = o[..., 0:-ph, 0:-pw]
                 o = net(x[..., 0:hh, W // 2 - pw:].contiguous(), nm).float(); out[..., 0:H // 2, W // 2:] = o[..., 0:-ph, pw:]
                 o = net(x[..., H // 2 - ph:, 0:ww].contiguous(), nm).float(); out[..., H // 2:, 0:W // 2] = o[..., ph:, 0:-pw]
                 o = net(x[..., H // 2 - ph:, W // 2 - pw:].contiguous(), nm).float(); out[..., H // 2:, W // 2:] = o[..., ph:, pw:]
+                if dio is not None:
+                    gt_dev = dio.upload_u8(gts)
+                    gpu_psnr, gpu_ssim = dio.psnr(out, gt_dev), dio.ssim(out, gt_dev)
             t1 = time.time()
-            imgs = (out.clamp(0, 1.0) * 255).permute(0, 2, 3, 1).cpu().numpy()
+            imgs = None
+            if gpu_psnr is None or args.save_image:       # host metrics (--cpu_io) or PNG output: the frames have to come back
+                imgs = (out.float().clamp(0, 1.0) * 255).permute(0, 2, 3, 1).cpu().numpy()
             base = frame_base[(v, kk)]
-            for e in range(imgs.shape[0]):
+            for e in range(out.shape[0]):
                 p = gpu_psnr[e] if gpu_psnr is not None else psnr_255(imgs[e], gts[e])
-                s = ssim_calculate(imgs[e], gts[e])
+                s = gpu_ssim[e] if gpu_ssim is not None else ssim_calculate(imgs[e], gts[e])
                 records.append((names.index(v), base + e, p, s))
                 if args.save_image:
                     import cv2
@@ -303,6 +334,7 @@ def add_common_args(parser):
     parser.add_argument("--model_path", type=str, default=None)
     parser.add_argument("--result_path", type=str, default=None)
     parser.add_argument("--cpu_io", action="store_true", help="reference-style host I/O: float conversion and PSNR on the CPU")
+    parser.add_argument("--device_noise", action="store_true", help="denoise: draw the AWGN on the GPU instead of the host")
     parser.add_argument("--random_weights", action="store_true", help="run without a checkpoint on the seeded synthetic weights")
     parser.add_argument("--synthetic", type=int, default=0, help="number of synthetic videos (no dataset needed)")
     parser.add_argument("--synthetic_frames", type=int, default=12)

@@ -15,7 +15,7 @@ EXPORTS = [
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
     "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
-    "gsn_cab_dense_tiles", "gsn_cab_dense", "gsn_u8_to_clip", "gsn_psnr_sse_blocks", "gsn_psnr_sse",
+    "gsn_cab_dense_tiles", "gsn_cab_dense", "gsn_u8_to_clip", "gsn_psnr_sse_blocks", "gsn_psnr_sse", "gsn_ssim_blocks", "gsn_ssim_workspace_bytes", "gsn_ssim",
 ]
 
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
@@ -107,6 +107,10 @@ def load():
     lib.gsn_u8_to_clip.argtypes = [vp, i, i, i, i, vp, vp]
     lib.gsn_psnr_sse_blocks.argtypes = []
     lib.gsn_psnr_sse.argtypes = [vp, i, vp, i, i, i, vp, vp]
+    lib.gsn_ssim_blocks.argtypes = []
+    lib.gsn_ssim_workspace_bytes.argtypes = [i, i, i]
+    lib.gsn_ssim_workspace_bytes.restype = ll
+    lib.gsn_ssim.argtypes = [vp, i, vp, i, i, i, vp, vp, vp]
     for n in EXPORTS:
         getattr(lib, n)       # every symbol include/shiftnet_b200.h declares must resolve (AttributeError otherwise)
     _lib = lib

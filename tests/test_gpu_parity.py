@@ -390,6 +390,38 @@ def test_device_io_u8_clip_and_psnr(dtype):
     assert all(p > 120 or p == float("inf") for p in same)     # float32 x/255*255 is exact or off by one ulp
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_device_ssim_matches_scipy(dtype):
+    """gsn_ssim against the reference's ssim_calculate (scipy gaussian_filter over the (3,H,W) array, inference/test_deblur_small.py:
+    25-49) to 1e-6, on ragged sizes incl. one narrower than the 13-tap window, values outside [0,1]."""
+    infer = gio.pkg("host.infer")
+    dio = infer.DeviceIO(torch.device(DEV))
+    g = np.random.default_rng(5)
+    for T, H, W in ((3, 37, 53), (2, 64, 96), (1, 9, 7)):
+        gts = [g.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(T)]
+        ref = torch.from_numpy(np.stack(gts)).permute(0, 3, 1, 2).float().div(255)
+        out = (ref + 0.08 * torch.from_numpy(g.standard_normal(ref.shape).astype(np.float32))).to(dtype)
+        got = dio.ssim(out.to(DEV), dio.upload_u8(gts))
+        imgs = (out.float().clamp(0, 1.0).permute(0, 2, 3, 1).numpy() * 255)
+        for e in range(T):
+            want = infer.ssim_calculate(imgs[e], gts[e])
+            assert abs(got[e] - want) <= 1e-6, (T, H, W, e, got[e], want)
+
+
+def test_denoise_entry_point_device_io_matches_host_io(tmp_path):
+    """The denoise entry point with the device I/O path (uint8 H2D, PSNR and SSIM on the GPU) and with --cpu_io print the same
+    metrics (same seeded host noise on both paths)."""
+    import subprocess
+    outs = []
+    for extra in ([], ["--cpu_io"]):
+        r = subprocess.run([sys.executable, os.path.join(gio.ROOT, "inference", "test_denoise_small.py"), "--synthetic", "1",
+                            "--sigma", "30", "--synthetic_frames", "9", "--synthetic_h", "96", "--synthetic_w", "128",
+                            "--result_path", str(tmp_path)] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("# ")])
+    assert outs[0] == outs[1] and len(outs[0]) == 3, outs
+
+
 def test_inference_entry_point_device_io_matches_host_io(tmp_path):
     """The deblur entry point with the device I/O path (default) and with --cpu_io print the same metrics."""
     import subprocess
