@@ -233,6 +233,79 @@ def gpu_eager_baseline(arch, sd, spec, x_dev, nm_dev, out_frames, steps=3):
     return res
 
 
+def run_strong(args, net, spec, rank, world, dev, dist):
+    """--scaling strong: ONE clip, its frames split across the ranks (host/tshard.py); before every CAB2 each rank receives one
+    boundary frame's half of the channels from its ring neighbour (NCCL send/recv over NVLink).  value = restored frames of the
+    whole clip / max-over-ranks time."""
+    Tn, Hh, Ww = args.frames, args.height, args.width
+    out_frames = Tn - 2 * CTX
+    _, x = pkg("host.synth").synthetic_clip(Tn, Hh, Ww, seed=7)          # the same clip on every rank
+    ts = pkg("host.tshard").TShard(rank, world, Tn)
+    x_host = x[:, ts.a:ts.b].half().contiguous().pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    lo, hi = ts.local_output_range(CTX, CTX)
+    out_host = torch.empty(hi - lo, 3, Hh, Ww, dtype=torch.float16).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        net.forward_tsharded(x_dev, ts)
+    barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ts.halo_bytes = ts.exchanges = 0
+    l0 = net.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        net.forward_tsharded(x_dev, ts)
+    e1.record()
+    barrier()
+    launches = net.kernel_launches - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    halo_per_step = ts.halo_bytes / args.steps
+    nx = ts.exchanges // args.steps
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        o = net.forward_tsharded(x_host.to(dev, non_blocking=True), ts)
+        out_host.copy_(o, non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    # one more step with CUDA events around every exchange: time spent in the halo traffic
+    ts.time_exchanges, ts.events = True, []
+    net.forward_tsharded(x_dev, ts)
+    torch.cuda.synchronize()
+    ms_x = sum(a.elapsed_time(b) for a, b in ts.events)
+    sampler.stop_flag = True
+    t_all = torch.tensor([ms, ms_e2e, ms_x], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_x = t_all.tolist()
+    if rank == 0:
+        emit({
+            "metric": METRIC, "value": out_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.arch} synthetic {Hh}x{Ww} one_len={out_frames}, ONE clip (1,{Tn},3,{Hh},{Ww}) T-sharded over {world} rank(s)",
+                       "sharding": f"frames of one clip x{world} (rank 0 owns {ts.n_local}), halo exchange before every CAB2, eager launches",
+                       "l2": "activations larger than L2, no flush needed", "accumulate": "fp32", "storage": "fp16 NHWC"},
+            "e2e": {"value": out_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 2 * world,
+                    "d2h_bytes_per_step": out_frames * 3 * Hh * Ww * 2, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches) * world,
+            "halo": {"exchanges_per_step": nx, "bytes_sent_per_rank_per_step": halo_per_step, "ms_in_exchanges_per_step": ms_x,
+                     "achieved_gbs_per_direction": halo_per_step / 1e9 / max(ms_x * 1e-3, 1e-12),
+                     "reference_gbs": 770.0, "note": "NCCL send/recv of C/2 channels of one boundary frame per CAB2 (48 per forward)"},
+            "clocks": sampler.summary(),
+        })
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,6 +317,8 @@ def main():
     ap.add_argument("--arch", default=ARCH, help="other BASELINE configs: gshift_deblur1 (Ours+), gshift_denoise2, gshift_denoise1")
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one clip per rank (default); strong: ONE clip T-sharded across the ranks with halo exchange over NVLink")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,6 +357,9 @@ def main():
         net = lambda inp: _net(inp, nm_dev)          # noqa: E731  (the noise map is a constant, it stays on the device)
     else:
         _, x = pkg("host.synth").synthetic_clip(Tn, Hh, Ww, seed=7 + rank)
+    if args.scaling == "strong":
+        run_strong(args, _net, spec, rank, world, dev, dist)
+        return
     x_host = x.half().pin_memory()
     x_dev = x_host.to(dev, non_blocking=True)
     out_host = torch.empty(out_frames, 3, Hh, Ww, dtype=torch.float16).pin_memory()

@@ -36,6 +36,7 @@ class Engine:
         # gsn_shift_conv1 -> gsn_ln_planar instead (cross-check in the tests).
         self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
         self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
+        self.tshard = None             # host/tshard.py TShard: this engine holds only a slice of the clip's frames
         self._a1_next = None
         # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
         self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"
@@ -264,7 +265,13 @@ class Engine:
                                       fw["du0"].shape[0], fw["w3"].data_ptr(), fw["beta"].data_ptr(),
                                       fw["bias3"].data_ptr() if fw["bias3"] is not None else None, Cc, T, weff.data_ptr(),
                                       beff.data_ptr(), self._stream()), "cab_fold")
-        out = self._new(T, H, W, Cc)
+        if self.tshard is not None and mode == L.MODE_CAB1:
+            # T-sharded clip: the next CAB2 needs a halo frame behind this rank's frames -- leave room for it (no copy later)
+            full = self._new(T + 1, H, W, Cc)
+            out = full[:T]
+            out._gsn_full = full
+        else:
+            out = self._new(T, H, W, Cc)
         b = L.CabPassB()
         b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
         b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
@@ -417,10 +424,25 @@ class Engine:
 
     def shift_block(self, p, x):
         """Encoder_shift_block.forward (gshift_deblur2.py:521-530): alternating fwd/rev (shift, CAB2, CAB1) pairs."""
+        ts = self.tshard
         for i in range(self.spec.pairs):
             q = f"{p}.{_PAIRS[i]}"
             fuse = self.ln_fuse and x.shape[-1] == 64
-            x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if (i & 1) else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
+            rev = bool(i & 1)
+            if ts is not None:
+                # this rank's n frames + the neighbour's boundary frame behind them (host/tshard.py): the kernels' circular indexing
+                # over n+1 frames then finds frame 0's predecessor / frame n-1's successor at index n
+                n = x.shape[0]
+                full = getattr(x, "_gsn_full", None)
+                if full is None or full.shape[0] != n + 1:
+                    full = self._new(n + 1, *x.shape[1:])
+                    full[:n].copy_(x)
+                ts.halo_into(full, n, rev)
+                y = self.gated_cab(q + ".0", full, L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
+                a1 = self._a1_next[:n] if (fuse and self._a1_next is not None) else None   # planar operand is frame-major: prefix view
+                x = self.gated_cab(q + ".1", y[:n], L.MODE_CAB1, a1_pre=a1)
+                continue
+            x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
             x = self.gated_cab(q + ".1", x, L.MODE_CAB1, a1_pre=self._a1_next if fuse else None)
         return x
 
@@ -521,8 +543,17 @@ class Engine:
         m = 8 if sp.plus else 4
         if H % m or W % m:
             raise ValueError(f"H and W must be multiples of {m} for {sp.name} (got {H}x{W}); the reference scripts crop/pad to that")
-        if T - past - future <= 0:
-            raise ValueError("clip too short for the requested past/future context")
+        ts = self.tshard
+        if ts is not None:
+            if not sp.circular or sp.plus or sp.denoise:
+                raise ValueError("T-sharded mode needs a net whose temporal roll wraps around the clip (gshift_deblur2)")
+            if T != ts.n_local:
+                raise ValueError(f"T-sharded mode: this rank owns {ts.n_local} frames, got {T}")
+            lo, hi = ts.local_output_range(past, future)
+        else:
+            if T - past - future <= 0:
+                raise ValueError("clip too short for the requested past/future context")
+            lo, hi = past, T - future
         dt = L.DTYPE_F16 if xin.dtype == torch.float16 else L.DTYPE_F32
         n0 = sp.n0
         n0p = P.pad8(n0)
@@ -557,7 +588,9 @@ class Engine:
         dec = self.stage1("stage1", holder)
         del holder
         # stage 2 on the centre frames only (gshift_deblur2.py:738-746,755)
-        s = slice(past, T - future)
+        s = slice(lo, hi)
+        if hi <= lo:                  # T-sharded: all of this rank's frames are context frames of the clip
+            return torch.empty(0, 3, H, W, dtype=xin.dtype, device=self.dev)
         third = sam[s] if sp.denoise else sam0[s]
         y = self.conv("rconcat", [x0[s], third, dec[s]], [n0, n0, n0], n0,
                       prelu_key="lrelu.weight" if sp.denoise else None)
@@ -567,9 +600,9 @@ class Engine:
             r = self.tfr_unet(f"rorb{i}", r)
         if not sp.denoise:
             r = self.add(r, y)
-        To = T - past - future
+        To = hi - lo
         out = torch.empty(To, 3, H, W, dtype=xin.dtype, device=self.dev)
         wo = self.cache["out"]
         L.check(self.lib.gsn_conv_out(r.data_ptr(), n0p, self.sd["conv_last.weight"].shape[-1], wo.data_ptr(),
-                                      xin[past:].data_ptr(), cin, dt, To, H, W, out.data_ptr(), self._stream()), "conv_out")
+                                      xin[lo:].data_ptr(), cin, dt, To, H, W, out.data_ptr(), self._stream()), "conv_out")
         return out

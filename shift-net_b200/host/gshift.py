@@ -86,5 +86,24 @@ class GShiftNetB200(nn.Module):
         return out_s.clone()
 
 
+    @torch.no_grad()
+    def forward_tsharded(self, x_local, tshard):
+        """One slice of a T-sharded clip (host/tshard.py): x_local (1, n_local, 3, H, W) are the frames this rank owns; returns the
+        restored frames among them (the clip's context frames are cropped on the ranks that hold them).  Launches eagerly: the
+        halo exchanges are NCCL point-to-point operations between the kernels."""
+        if not x_local.is_cuda:
+            raise RuntimeError("shiftnet_b200.GShiftNet runs on CUDA (B200, sm_100a) only; there is no CPU fallback")
+        eng = self.engine()
+        lib = eng.lib
+        eng.tshard = tshard
+        try:
+            l0 = lib.gsn_launch_count()
+            out = eng.forward(x_local, None, past=self.num_fb, future=self.num_ff)
+            self.kernel_launches += lib.gsn_launch_count() - l0
+        finally:
+            eng.tshard = None
+        return out
+
+
 def make_arch(arch_name):
     return type("GShiftNet", (GShiftNetB200,), {"arch": arch_name, "__doc__": GShiftNetB200.__doc__})

@@ -1,0 +1,77 @@
+"""T-sharded single-clip mode: ONE clip's frames are split across the ranks of a torchrun launch,
+so a long / high-resolution clip uses all GPUs of the box instead of one.
+
+Everything in GShiftNet.forward is per-frame except the half-channel temporal roll in front of every CAB2
+(channel_shift, gshift_deblur2.py:499-519): frame t reads C/2 channels of frame t-1 (forward pairs) or t+1 (reverse pairs).
+Each rank therefore needs, before every CAB2, ONE boundary frame's half of the channels from its ring neighbour: the halo
+exchange below (NCCL send/recv over NVLink on GPUs; gloo in the CPU tests).  48 exchanges per forward for Ours-s, 14.7 MB each
+at 720p level 1.  Supported for the nets whose roll wraps around the clip (Ours-s deblur, gshift_deblur2.py:504-505): the ring of
+ranks closes the wrap.
+
+The halo frame is stored BEHIND the rank's own frames, at index Tl of a (Tl+1)-frame buffer: with the kernels' circular
+indexing over Tl+1 frames, frame 0's predecessor is index Tl and frame Tl-1's successor is index Tl, so the unmodified
+single-GPU kernels compute every own frame correctly (the halo frame's own output is discarded).
+"""
+from __future__ import annotations
+
+import torch
+
+
+def split_frames(T: int, world: int, rank: int):
+    """Contiguous, balanced split of T frames: rank r owns [a, b)."""
+    base, rem = divmod(T, world)
+    a = rank * base + min(rank, rem)
+    return a, a + base + (1 if rank < rem else 0)
+
+
+class TShard:
+    def __init__(self, rank: int, world: int, T_global: int, group=None):
+        self.rank, self.world, self.T, self.group = rank, world, T_global, group
+        self.a, self.b = split_frames(T_global, world, rank)
+        self.halo_bytes = 0          # bytes this rank SENT in halo exchanges (statistics for bench.py)
+        self.exchanges = 0
+        self.events = []             # (start, end) CUDA event pairs around the exchanges, when timing is on
+        self.time_exchanges = False
+
+    @property
+    def n_local(self):
+        return self.b - self.a
+
+    def exchange(self, send: torch.Tensor, reverse: bool) -> torch.Tensor:
+        """Ring exchange of one contiguous halo tensor.  forward pairs: every rank sends to rank+1 and receives from rank-1;
+        reverse pairs: sends to rank-1, receives from rank+1.  Returns the received tensor (same shape / dtype)."""
+        self.exchanges += 1
+        self.halo_bytes += send.numel() * send.element_size()
+        if self.world == 1:
+            return send                                  # the ring of one rank: its own boundary frame is the wrap-around
+        import torch.distributed as dist
+        dst = (self.rank + (-1 if reverse else 1)) % self.world
+        src = (self.rank + (1 if reverse else -1)) % self.world
+        recv = torch.empty_like(send)
+        ev = None
+        if self.time_exchanges and send.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        ops = [dist.P2POp(dist.isend, send, dst, self.group), dist.P2POp(dist.irecv, recv, src, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if ev is not None:
+            ev[1].record()
+            self.events.append(ev)
+        return recv
+
+    def halo_into(self, full: torch.Tensor, n: int, reverse: bool) -> None:
+        """full: (n+1, H, W, C) NHWC buffer holding this rank's n frames in [:n]; fills the half of frame n that the CAB2 of the
+        given direction reads from the neighbour: forward -> channels [C/2, C) of the previous rank's LAST frame,
+        reverse -> channels [0, C/2) of the next rank's FIRST frame."""
+        h = full.shape[-1] // 2
+        if reverse:
+            full[n, :, :, :h] = self.exchange(full[0, :, :, :h].contiguous(), True)
+        else:
+            full[n, :, :, h:] = self.exchange(full[n - 1, :, :, h:].contiguous(), False)
+
+    def local_output_range(self, past: int, future: int):
+        """Own frames that survive the net's final crop of `past` / `future` context frames of the GLOBAL clip, as a local slice."""
+        lo = max(past - self.a, 0)
+        hi = self.n_local - max(self.b - (self.T - future), 0)
+        return lo, max(hi, lo)

@@ -268,6 +268,32 @@ def test_full_forward_at_benchmark_size_vs_oracle(case):
     _contract(out, ref, gt, x, name)
 
 
+# ------------------------------------------------------------------------------------------------ T-sharded single clip
+def test_tshard_single_rank_equals_plain_forward():
+    """host/tshard.py with a ring of ONE rank: the halo behind the clip is the clip's own wrap-around frame, so the T-sharded code
+    path (halo buffers, n+1-frame CAB2 launches, prefix views for CAB1, local crop) must reproduce net(x) bit-exactly."""
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
+    net = importlib.import_module("basicsr.models.archs.gshift_deblur2").GShiftNet(future_frames=2, past_frames=2)
+    net.load_state_dict(sd)
+    net = net.half().to(DEV).eval()
+    _, x = gio.pkg("host.synth").synthetic_clip(7, 96, 128)
+    x = x.half().to(DEV)
+    ts = gio.pkg("host.tshard").TShard(0, 1, 7)
+    a = net.forward_tsharded(x, ts)
+    b = net(x)
+    assert ts.exchanges == 48 and torch.equal(a, b)
+
+
+def test_tshard_two_ranks_nccl_bit_exact():
+    """One clip across 2 GPUs (torchrun, NCCL send/recv halo exchange): gathered output == single-GPU forward, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(gio.ROOT, "scripts", "tshard_check.py"), "9", "96", "128"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BIT-EXACT" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 # ------------------------------------------------------------------------------------------------ multi-GPU entry point
 def test_inference_entry_point_two_ranks_nccl(tmp_path):
     """inference/test_deblur_small.py under torchrun on 2 GPUs: units shard across ranks, ONE NCCL all_gather of the

@@ -112,3 +112,58 @@ def test_denoise_chunking_numbers_frames_with_a_running_index():
     assert infer.frame_bases(units) == {("a", 0): 0, ("a", 1): 51, ("b", 0): 0}
     units = infer.plan_units({"c": (list(range(40)), list(range(40)))}, "deblur", 8)
     assert infer.frame_bases(units) == {("c", k): 8 * k for k in range(4)}
+
+
+def _halo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts_mod = gio.pkg("host.tshard")
+    T, C = 11, 8
+    ts = ts_mod.TShard(rank, world, T)
+    n = ts.n_local
+    # frame f of the global clip holds the value 100 f + channel
+    glob = (100.0 * torch.arange(T).view(T, 1, 1, 1) + torch.arange(C).view(1, 1, 1, C)).expand(T, 2, 3, C).contiguous()
+    full = torch.full((n + 1, 2, 3, C), -1.0)
+    full[:n] = glob[ts.a:ts.b]
+    ts.halo_into(full, n, reverse=False)
+    fwd = full[n].clone()
+    ts.halo_into(full, n, reverse=True)
+    rev = full[n].clone()
+    q.put((rank, ts.a, ts.b, fwd[0, 0].tolist(), rev[0, 0].tolist(), ts.local_output_range(2, 2), ts.halo_bytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tshard_halo_ring_gloo_world3():
+    """T-sharded single-clip mode (host/tshard.py): the forward halo is the HIGH half of the previous rank's last frame, the reverse
+    halo the LOW half of the next rank's first frame, both around the ring (the clip's circular wrap); the final crop of the
+    clip's context frames lands on the ranks that hold them."""
+    world, T, C = 3, 11, 8
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    spans = [(g[1], g[2]) for g in got]
+    assert spans == [(0, 4), (4, 8), (8, 11)]
+    kept = 0
+    for rank, a, b, fwd, rev, (lo, hi), nbytes in got:
+        prev_last, next_first = (a - 1) % T, b % T
+        assert fwd[C // 2:] == [100.0 * prev_last + c for c in range(C // 2, C)]          # forward: high half of frame a-1
+        assert rev[:C // 2] == [100.0 * next_first + c for c in range(C // 2)]             # reverse: low half of frame b
+        assert nbytes == 2 * (2 * 3 * C // 2) * 4
+        kept += hi - lo
+        assert [a + i for i in range(lo, hi)] == [f for f in range(a, b) if 2 <= f < T - 2]
+    assert kept == T - 4
+
+
+def test_tshard_single_rank_ring_is_the_circular_wrap():
+    ts = gio.pkg("host.tshard").TShard(0, 1, 5)
+    full = torch.arange(6 * 1 * 1 * 4, dtype=torch.float32).view(6, 1, 1, 4)
+    full[5] = -1
+    ts.halo_into(full, 5, reverse=False)
+    assert full[5, 0, 0].tolist() == [-1, -1, 18, 19]          # high half of its own last frame (frame 4)
+    ts.halo_into(full, 5, reverse=True)
+    assert full[5, 0, 0].tolist() == [0, 1, 18, 19]            # low half of its own first frame
