@@ -182,7 +182,7 @@ def test_conv_in_out(env):
     x = torch.rand(T, 3, H, W, generator=g)
     for dt, tdt in ((L.DTYPE_F16, torch.float16), (L.DTYPE_F32, torch.float32)):
         xd = x.to(DEV, tdt).contiguous()
-        wi, bi = P.pack_conv_in(eng.sd["feat_extract.0.weight"], eng.sd["feat_extract.0.bias"], 16)
+        wi, bi = eng._up(P.pack_conv_in(eng.sd["feat_extract.0.weight"], eng.sd["feat_extract.0.bias"], 16))   # packed on the host
         f0 = torch.empty(T, H, W, 16, dtype=torch.float16, device=DEV)
         L.check(eng.lib.gsn_conv_in(xd.data_ptr(), dt, T, 3, H, W, wi.data_ptr(), bi.data_ptr(), 16, f0.data_ptr(), eng._stream()))
         ref = F.conv2d(xd.float().cpu(), sd["feat_extract.0.weight"], sd["feat_extract.0.bias"], padding=1)
@@ -190,7 +190,7 @@ def test_conv_in_out(env):
         assert f0[..., 14:].abs().max().item() == 0.0
         # conv_out: 5x5 14->3 + residual
         feat = torch.randn(T, 14, H, W, generator=g)
-        wo = P.pack_conv_out(eng.sd["conv_last.weight"], 16)
+        wo = eng._up(P.pack_conv_out(eng.sd["conv_last.weight"], 16))
         out = torch.empty(T, 3, H, W, dtype=tdt, device=DEV)
         fd = to_nhwc(feat)
         L.check(eng.lib.gsn_conv_out(fd.data_ptr(), 16, 5, wo.data_ptr(), xd.data_ptr(), 3, dt, T, H, W, out.data_ptr(), eng._stream()))
