@@ -37,6 +37,9 @@ class Engine:
         self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
         self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
         self.tshard = None             # host/tshard.py TShard: this engine holds only a slice of the clip's frames
+        # HFMA2/HMUL2 thread-instructions per pixel of the 16x16-tile pass A (its two depthwise stages: 15.1 k warp-instructions per
+        # 256-pixel tile incl. the halo recompute): bench.py reports the kernel against the FMA pipe with it
+        self.pass_a_hfma2_per_pixel = 15.1e3 * 32 / 256
         self._a1_next = None
         # dense CAB bodies (16 / 24 stored channels): conv-PReLU-conv fused in one kernel (GSN_CAB_FUSED=0: two conv launches)
         self.cab_fused = os.environ.get("GSN_CAB_FUSED", "1") == "1"

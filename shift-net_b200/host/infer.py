@@ -323,6 +323,7 @@ def run(net_cls, task, args):
     res = summarize(records, names, task, log.write_log)
     if world > 1 and dist.is_initialized():
         dist.barrier()
+        dist.destroy_process_group()
     return res, records
 
 
