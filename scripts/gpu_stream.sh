@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_stream.py -x -q -s > gpurun_out/stream_test.log 2>&1; echo "pytest exit $?" >> gpurun_out/stream_test.log
 grep -E "\[stream\]|passed|failed|Error|error|exit|trap|illegal" gpurun_out/stream_test.log | head -60
 if grep -q "pytest exit 0" gpurun_out/stream_test.log; then
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/stream_bench.json 2> gpurun_out/stream_bench.err
+  GSN_PASS_A_STREAM=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/stream_bench.json 2> gpurun_out/stream_bench.err
   python - <<PY
 import json
 try:

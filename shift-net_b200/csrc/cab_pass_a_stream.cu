@@ -10,16 +10,16 @@
 //   * Warp roles, all running concurrently on different rows of the stream and handing off through mbarrier rings (every wait
 //     is a hardware-suspended mbarrier.try_wait, nobody polls):
 //       warps 0-7   dwA : RepConv2 (dw3x3 + id) on both halves + SimpleGate, one warp per chunk pair; lanes = (half, pixel pair),
-//                         the two halves of a pixel meet through one shuffle; depthwise taps live in registers for the whole
-//                         kernel.  Between steps the same warps run SimpleGate2 on GEMM2's accumulators of three steps ago
-//                         (warp = TMEM lane quarter x channel half): z -> swizzled staging -> TMA store, and the per-piece
-//                         channel sums of z (deterministic)
+//                         the two halves of a pixel meet through one shuffle; depthwise taps live in registers for the whole kernel
 //       warps 8-15  dwB : RepConv (merged 5x5) on the gated tensor, one warp per chunk; lanes = (4-channel half chunk, pixel pair),
 //                         25 taps in registers, five sliding accumulator rows; writes GEMM2's A operand; the warp that
 //                         completes a block issues GEMM2
-//       warps 16-19 drain: one warp per TMEM lane quarter = per row of the step: GEMM1's accumulators -> fp16 row ring;
-//                         lane 0 of warp 19 also issues the TMA loads of the operand rows (two steps ahead) and GEMM1 (one
-//                         step ahead) at the points of its loop where their inputs are known to be free
+//       warps 16-19 aux : one warp per TMEM lane quarter = per row of the step: drains GEMM1's accumulators to the fp16 row ring;
+//                         lane 0 of warp 19 also issues the TMA loads of the operand rows (two steps ahead) and GEMM1 (one step
+//                         ahead) at the points of its loop where their inputs are known to be free
+//       gate stage      : SimpleGate2 on GEMM2's accumulators a few steps later (z -> swizzled staging -> TMA store by the last
+//                         task to finish, plus the deterministic per-piece channel sums of z) is split into 12 tasks per block:
+//                         each aux warp takes half the channels of its row, the two dwA warps of that lane quarter a quarter each
 //     GEMM1 / GEMM2 are tcgen05.mma (M=128, N=128, K=16) with fp32 accumulators in TMEM (2 + 2 slots of 128 columns).
 //     20 warps = 5 per scheduler = 96 registers per thread (a 21st warp would cost every thread 16 registers).
 //   * Work is cut into equal contiguous runs of 4-row blocks per CTA (a run may span several strips / frames): no tail wave.
@@ -159,6 +159,127 @@ __device__ __forceinline__ bool last_arrival(uint32_t cnt_addr, uint32_t n) {
   return old == n - 1;      // inc wraps to 0 at n-1: the counter is ready for its next use
 }
 
+// One warp's share of the gate stage of a block (4 output rows x 26 pixels): SimpleGate2 z = a * sigmoid(b) on GEMM2's accumulators
+// of TMEM lane quarter gq (= output row gq of the block) for NCH channel chunks starting at chunk c0 -> fp16 z in the swizzled
+// staging tile; the per-piece channel sums of those channels; the last of the 12 tasks of a block issues the TMA store.
+template <int KC1, int NCH>
+struct GateTask {
+  using K = StCfg<KC1>;
+  StCur cz;            // lagging cursor over the CTA's steps
+  uint32_t v, np;      // valid blocks gated, pieces flushed
+  int gq, c0, sum_px0, sum_off;
+  float ps[8];         // lane (kq = lane & 7, cq = lane >> 3 < NCH): sums of channels 8 (c0 + cq) + 0..7 over its pixels of the piece
+
+  __device__ __forceinline__ void init(const StSched &sc, const StGeom &geo, int gq_, int c0_, int lane) {
+    cz.start(sc, geo.nstrips);
+    v = np = 0;
+    gq = gq_;
+    c0 = c0_;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ps[e] = 0.f;
+    // sums read the staging tile back: lane (kq, cq) reads the pixels of row gq whose staging index is == kq mod 8 (three or four
+    // of the row), so its swizzled chunk position is a per-lane constant and a quarter warp hits 8 different 16-byte columns
+    sum_px0 = ((lane & 7) - gq * K::TW) & 7;
+    sum_off = (gq * K::TW + sum_px0) * 128 + (((c0 + (lane >> 3)) ^ (lane & 7)) << 4);
+  }
+
+  __device__ __forceinline__ void run(unsigned char *smem, uint32_t sbase, uint32_t tmem, const GsnCabPassA &d, const StGeom &geo,
+                                      const CUtensorMap *tm_z, int lane) {
+    constexpr int C = K::C;
+    if (!cz.live) return;
+    if (cz.k >= 2) {
+      const uint32_t bar0 = sbase + K::S_BAR;
+      const int t = cz.t, sx = cz.sx;
+      const int x0 = sx * K::TW, yb = (cz.s.off + cz.k - 2) * 4;
+      const uint32_t zs = v & 1, zph = (v >> 1) & 1;
+      mbar_wait_nt(bar0 + 8 * (B_G2F + zs), zph);
+      tc_fence_after();
+      mbar_wait_nt(bar0 + 8 * (B_ZFREE + zs), zph ^ 1);     // the store of two blocks ago has read this staging buffer
+      unsigned char *zt = smem + K::S_Z + zs * K::Z_STRIDE;
+      const uint32_t tlane = (uint32_t)(gq * 32) << 16;
+      const int pz = gq * K::TW + lane;
+#pragma unroll
+      for (int grp = 0; grp < NCH; ++grp) {
+        uint32_t a[8], b[8];
+        const uint32_t ta = tmem + tlane + 256 + zs * K::N + (c0 + grp) * 8;
+        tmem_ld8_nowait(ta, a);
+        tmem_ld8_nowait(ta + C, b);
+        tmem_ld_wait();
+        float z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(__uint_as_float(b[i])));
+          z[i] = fmaf(__uint_as_float(a[i]), th, __uint_as_float(a[i]));     // W2 is held at half scale: (a/2) tanh(b/2) + a/2
+        }
+        if (lane < K::TW) *reinterpret_cast<uint4 *>(zt + pz * 128 + (((c0 + grp) ^ (pz & 7)) << 4)) = pack8(z);
+      }
+      tc_fence_before();
+      __syncwarp();        // also: this warp's staging writes are visible to its own lanes
+      if (lane == 0) mbar_arrive(bar0 + 8 * (B_G2E + zs));   // the accumulator slot may take the GEMM2 of two blocks ahead
+      if (yb + gq < d.H && (lane >> 3) < NCH) {              // channel sums over the valid pixels (fp16 values, as pass B reads them)
+        int nvx = d.W - x0;
+        nvx = nvx > K::TW ? K::TW : nvx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (sum_px0 + 8 * i < nvx) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4 *>(zt + sum_off + i * 1024), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ps[e] += f[e];
+          }
+        }
+      }
+      fence_async_proxy();   // staging writes -> visible to the TMA store
+      __syncwarp();
+      bool last = false;
+      if (lane == 0) last = last_arrival(sbase + K::S_CNT + 4 * (N_Z + zs), 12);
+      if (last) {            // the twelfth task stores the tile; rows / columns beyond the image are clipped by the hardware
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::
+                         "l"(reinterpret_cast<uint64_t>(tm_z)), "r"(0), "r"(x0), "r"(yb), "r"(t), "r"(sbase + K::S_Z + zs * K::Z_STRIDE)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        mbar_arrive(bar0 + 8 * (B_ZFREE + zs));
+      }
+      __syncwarp();
+      ++v;
+      if (cz.k == cz.n - 1) {
+        // last block of the piece: its channel sums (fixed order => deterministic) -> chan_partial[t][strip * ppc + pidx][C]
+        float *red = reinterpret_cast<float *>(smem + K::S_RED);   // [4 rows][64 channels]
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], off);
+        mbar_wait(bar0 + 8 * B_RFREE, (np & 1) ^ 1);        // the previous piece's sums have left the buffer
+        if ((lane & 7) == 0 && (lane >> 3) < NCH) {
+          float *rp8 = red + gq * C + (c0 + (lane >> 3)) * 8;
+          *reinterpret_cast<float4 *>(rp8) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+          *reinterpret_cast<float4 *>(rp8 + 4) = make_float4(ps[4], ps[5], ps[6], ps[7]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ps[e] = 0.f;
+        __syncwarp();
+        bool lastr = false;
+        if (lane == 0) lastr = last_arrival(sbase + K::S_CNT + 4 * N_RED, 12);
+        lastr = __shfl_sync(0xffffffffu, lastr ? 1 : 0, 0) != 0;
+        if (lastr) {
+          const size_t slot = (size_t)t * geo.ntiles + (size_t)sx * geo.ppc + cz.s.pidx;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int ch = lane + 32 * hh;
+            d.chan_partial[slot * C + ch] = (red[ch] + red[C + ch]) + (red[2 * C + ch] + red[3 * C + ch]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * B_RFREE);
+        }
+        ++np;
+      }
+    }
+    cz.step();
+  }
+};
+
 template <int KC1>
 __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const GsnCabPassA d, const __grid_constant__ CUtensorMap tm_a1,
                                                                          const __grid_constant__ CUtensorMap tm_z, const StGeom geo) {
@@ -174,10 +295,12 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
   const unsigned char *wb = reinterpret_cast<const unsigned char *>(d.wblob);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + K::S_TMEM);
   constexpr uint32_t idesc = make_idesc_f16(128, K::N);
-  // the gate stage of a step runs LAG steps behind its dw3x3 rows: 2 gives the dw5x5 warps (at most 1.5 steps behind, the depth of
-  // the row ring) and GEMM2 just enough time, and hands the accumulator slot back one step earlier than 3 did (with 3 the dw5x5
-  // warps spent 28 % of their time waiting for GEMM2 of two steps ago, which itself waited for that slot)
-  constexpr uint32_t LAG = 2;
+  // The gate stage (SimpleGate2 on GEMM2's accumulators) of a block is shared: the aux warp of its row takes channel chunks 0..3,
+  // the two dw3x3 warps of that TMEM lane quarter chunks 4..5 and 6..7 (measured: all of it on the dw3x3 warps 0.70 ms per launch,
+  // all of it on the aux warps 0.73 ms -- either way the role that carried it was the critical path).  It runs LAG steps behind
+  // the role's own position: the drain is at most 1.5 steps (the row ring) ahead of the dw3x3 warps, those at most 1.5 steps ahead
+  // of the dw5x5 warps whose last row triggers GEMM2.
+  constexpr uint32_t LAG_D = 3, LAG_A = 2;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -187,7 +310,7 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
       mbar_init(bar(B_G1E + i), 4);   // the four drain warps
       mbar_init(bar(B_A2E + i), 1);   // tcgen05.commit after GEMM2 (or a plain arrive for warm-up blocks)
       mbar_init(bar(B_G2F + i), 1);   // tcgen05.commit after GEMM2
-      mbar_init(bar(B_G2E + i), 8);   // the eight gate warps
+      mbar_init(bar(B_G2E + i), 12);  // the twelve gate tasks of a block (4 aux warps + 8 dw3x3 warps)
       mbar_init(bar(B_ZFREE + i), 1); // the thread that stored the staging tile, once the TMA has read it
     }
     for (int i = 0; i < K::NPAIR; ++i) {
@@ -249,115 +372,11 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
     unsigned char *gtp = smem + K::S_GT + p * 512 + lane * 16;
     int s3 = 0;                      // row pair slot of both rings (they advance together)
     uint32_t ph3 = 0;
-    // gate stage (SimpleGate2 + z store + channel sums): this warp = TMEM lane quarter gq (= output row of the block) x channel half gh
-    const int gq = p & 3, gh = p >> 2;
-    const uint32_t tlane = (uint32_t)(gq * 32) << 16;
-    float *red = reinterpret_cast<float *>(smem + K::S_RED);   // [4 rows][64 channels]
-    // running channel sums of the piece: lane (kq, cq) holds channels 32 gh + 8 cq + 0..7 over its pixels (see the gate stage)
-    float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int sum_px0 = ((lane & 7) - gq * K::TW) & 7;                        // first pixel of the row with staging index == kq mod 8
-    const int sum_off = (gq * K::TW + sum_px0) * 128 + (((gh * 4 + (lane >> 3)) ^ (lane & 7)) << 4);
-    StCur cz;
-    cz.start(sc, geo.nstrips);
-    uint32_t v = 0, np = 0, gdone = 0;   // valid blocks gated, pieces flushed, steps whose rows are done
-
-    auto gate_stage = [&]() {
-      if (!cz.live) return;
-      if (cz.k >= 2) {
-        const int t = cz.t, sx = cz.sx;
-        const int x0 = sx * K::TW, yb = (cz.s.off + cz.k - 2) * 4;
-        const uint32_t zs = v & 1, zph = (v >> 1) & 1;
-        mbar_wait_nt(bar(B_G2F + zs), zph);
-        tc_fence_after();
-        mbar_wait_nt(bar(B_ZFREE + zs), zph ^ 1);       // the store of two blocks ago has read this staging buffer
-        unsigned char *zt = smem + K::S_Z + zs * K::Z_STRIDE;
-        const int pz = gq * K::TW + lane;
-#pragma unroll
-        for (int grp = 0; grp < 4; ++grp) {
-          uint32_t a[8], b[8];
-          const uint32_t ta = tmem + tlane + 256 + zs * K::N + gh * 32 + grp * 8;
-          tmem_ld8_nowait(ta, a);
-          tmem_ld8_nowait(ta + C, b);
-          tmem_ld_wait();
-          float z[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(__uint_as_float(b[i])));
-            z[i] = fmaf(__uint_as_float(a[i]), th, __uint_as_float(a[i]));
-          }
-          if (lane < K::TW) *reinterpret_cast<uint4 *>(zt + pz * 128 + (((gh * 4 + grp) ^ (pz & 7)) << 4)) = pack8(z);
-        }
-        tc_fence_before();
-        __syncwarp();        // also: this warp's staging writes are visible to its own lanes
-        if (lane == 0) mbar_arrive(bar(B_G2E + zs));     // the accumulator slot may take the GEMM2 of two blocks ahead
-        // channel sums over the valid pixels of this warp's row, read back from the staging tile (the fp16 values pass B will read).
-        // lane = (swizzle key kq = lane & 7, channel chunk cq = lane >> 3): it reads the pixels whose staging index is == kq mod 8
-        // (three or four of the row), so its swizzled chunk position is a per-lane constant and the 8 lanes of a quarter warp hit
-        // 8 different 16-byte columns; the cross-lane reduction waits for the end of the piece
-        if (yb + gq < d.H) {
-          int nvx = d.W - x0;
-          nvx = nvx > K::TW ? K::TW : nvx;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int px = sum_px0 + 8 * i;
-            if (px < nvx) {
-              float f[8];
-              unpack8(*reinterpret_cast<const uint4 *>(zt + sum_off + i * 1024), f);
-#pragma unroll
-              for (int e2 = 0; e2 < 8; ++e2) ps[e2] += f[e2];
-            }
-          }
-        }
-        fence_async_proxy();   // staging writes -> visible to the TMA store
-        __syncwarp();
-        bool last = false;
-        if (lane == 0) last = last_arrival(cnt(N_Z + zs), 8);
-        if (last) {            // the eighth warp stores the tile; rows / columns beyond the image are clipped by the hardware
-          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n" ::
-                           "l"(reinterpret_cast<uint64_t>(&tm_z)), "r"(0), "r"(x0), "r"(yb), "r"(t), "r"(sbase + K::S_Z + zs * K::Z_STRIDE)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-          mbar_arrive(bar(B_ZFREE + zs));
-        }
-        __syncwarp();
-        ++v;
-        if (cz.k == cz.n - 1) {
-          // last block of the piece: its channel sums (fixed order => deterministic) -> chan_partial[t][strip * ppc + pidx][C]
-#pragma unroll
-          for (int off = 1; off < 8; off <<= 1)
-#pragma unroll
-            for (int e2 = 0; e2 < 8; ++e2) ps[e2] += __shfl_xor_sync(0xffffffffu, ps[e2], off);
-          mbar_wait(bar(B_RFREE), (np & 1) ^ 1);       // the previous piece's sums have left the buffer
-          if ((lane & 7) == 0) {
-            float *rp8 = red + gq * C + gh * 32 + (lane >> 3) * 8;
-            *reinterpret_cast<float4 *>(rp8) = make_float4(ps[0], ps[1], ps[2], ps[3]);
-            *reinterpret_cast<float4 *>(rp8 + 4) = make_float4(ps[4], ps[5], ps[6], ps[7]);
-          }
-#pragma unroll
-          for (int e2 = 0; e2 < 8; ++e2) ps[e2] = 0.f;
-          __syncwarp();
-          bool lastr = false;
-          if (lane == 0) lastr = last_arrival(cnt(N_RED), 8);
-          lastr = __shfl_sync(0xffffffffu, lastr ? 1 : 0, 0) != 0;
-          if (lastr) {
-            const size_t slot = (size_t)t * geo.ntiles + (size_t)sx * geo.ppc + cz.s.pidx;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int ch = lane + 32 * hh;
-              d.chan_partial[slot * C + ch] = (red[ch] + red[C + ch]) + (red[2 * C + ch] + red[3 * C + ch]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_RFREE));
-          }
-          ++np;
-        }
-      }
-      cz.step();
-    };
-
     const uint32_t b_r1f = bar(B_R1F), b_r1e = bar(B_R1E), b_gtf = bar(B_GTF + p * K::NPAIR), b_gte = bar(B_GTE + p * K::NPAIR);
+    // this warp's share of the gate stage: TMEM lane quarter p & 3 (= output row of the block), channel chunks 4 + 2 (p >> 2) .. +1
+    GateTask<KC1, 2> gate;
+    gate.init(sc, geo, p & 3, 4 + 2 * (p >> 2), lane);
+    uint32_t gdone = 0;
     while (sc.next()) {
       const int t = sc.col / geo.nstrips, sx = sc.col - t * geo.nstrips;
       const int x0 = sx * K::TW, ys = sc.off * 4;
@@ -416,10 +435,10 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
           if (lane == 0) mbar_arrive(b_gtf + 8 * s3);
           if (++s3 == K::NPAIR) { s3 = 0; ph3 ^= 1; }
         }
-        if (++gdone > LAG) gate_stage();
+        if (++gdone > LAG_A) gate.run(smem, sbase, tmem, d, geo, &tm_z, lane);
       }
     }
-    for (uint32_t i = 0; i < LAG; ++i) gate_stage();
+    for (uint32_t i = 0; i < (gdone < LAG_A ? gdone : LAG_A); ++i) gate.run(smem, sbase, tmem, d, geo, &tm_z, lane);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   } else if (warp < 16) {
     // ================================================================ dwB: merged 5x5 on the gated tensor -> A2 (GEMM2 operand)
@@ -571,6 +590,9 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
       if (nsteps_total > 1) issue_tma();
       issue_gemm1(0);
     }
+    // ---- gate stage of the block LAG_D steps behind the drain: this warp = TMEM lane quarter q, channel chunks 0..3
+    GateTask<KC1, 4> gate;
+    gate.init(sc, geo, q, 0, lane);
 #pragma unroll 1
     for (uint32_t g = 0; g < nsteps_total; ++g) {
       // ---- drain step g: TMEM slot g&1, lanes [32q, 32q+32) = row q of the step -> G1 ring row (4g + q) % 6
@@ -618,7 +640,10 @@ __global__ void __launch_bounds__(kStThreads, 1) cab_pass_a_stream_kernel(const 
         mbar_arrive(bar(B_G1E + gs));     // TMEM slot free for the GEMM1 of step g+2
         mbar_arrive(bar(B_R1F + s3));     // row ready for the dwA warps (the pair completes with the neighbour warp's row)
       }
+      if (g >= LAG_D) gate.run(smem, sbase, tmem, d, geo, &tm_z, lane);   // block of step g - LAG_D
     }
+    for (uint32_t i = 0; i < (nsteps_total < LAG_D ? nsteps_total : LAG_D); ++i) gate.run(smem, sbase, tmem, d, geo, &tm_z, lane);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
