@@ -1,7 +1,7 @@
 """GPU parity suite (-m gpu): every CUDA op and the whole net, called through the C-ABI, against the CPU oracle
 (same seeded inputs) and against the committed reference goldens.  Tolerances: activations are stored in fp16
 (2^-11 relative per stage, fp32 accumulation), so single ops must agree to ~1e-3 relative RMS and the whole net to
->= 50 dB PSNR against the fp32 reference (the reference's own fp16 path reaches 66-68 dB)."""
+>= 60 dB PSNR against the fp32 reference (the reference's own fp16 path reaches 66-68 dB)."""
 import dataclasses
 import os
 import sys
@@ -332,7 +332,7 @@ def test_full_forward_golden(aenv, dtype):
     ref = torch.from_numpy(gold["full"])
     p = O.psnr(out.float().cpu(), ref)
     print(f"[parity] {spec.name} full forward {dtype}: PSNR vs reference fp32 = {p:.2f} dB")
-    assert p >= 50.0
+    assert p >= 60.0          # SURVEY.md section 8(c) contract; measured 68-84 dB
 
 
 def test_full_forward_k1_config_vs_oracle(env):
@@ -345,7 +345,7 @@ def test_full_forward_k1_config_vs_oracle(env):
     pg_ref, pg_out = O.psnr(ref.clamp(0, 1), gt[0, 2:-2]), O.psnr(out.clamp(0, 1), gt[0, 2:-2])
     drift = abs(pg_out - pg_ref) / pg_ref
     print(f"[parity] K1 256x256 T=8: PSNR(cuda, oracle)={p:.2f} dB ; PSNR-vs-GT ref={pg_ref:.4f} ours={pg_out:.4f} drift={drift:.2e}")
-    assert p >= 50.0 and drift <= 1e-3
+    assert p >= 60.0 and drift <= 1e-3
 
 
 def test_full_size_cyclic_frame_equivariance(env):
