@@ -251,11 +251,11 @@ def run_strong(args, net, spec, rank, world, dev, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(dev.index)        # started before the warm-up: a T-sharded step is tens of milliseconds, and the warm-up
+    sampler.start()                          # runs the same load (nvidia-smi needs ~0.1-0.3 s per sample on an 8-GPU box)
     for _ in range(args.warmup):
         net.forward_tsharded(x_dev, ts)
     barrier()
-    sampler = ClockSampler(dev.index)
-    sampler.start()
     ts.halo_bytes = ts.exchanges = 0
     l0 = net.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
