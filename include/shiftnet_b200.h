@@ -251,6 +251,11 @@ int gsn_shift_ln(const void *x, int T, int H, int W, int C, int mode, int circul
  * w1p: fp16 [K/8 padded to even][2C][8] (k-chunk planar, zero-padded K); ln: fp32 gamma[cin], beta[cin]. */
 int gsn_ln_pw(const void *x, const void *hw_pre, int T, int H, int W, int C, int mode, int circular, const float *ln,
               const void *w1p, void *ga, void *gb, void *stream);
+/* The same stage on TMA + tcgen05 (C = 80): the LayerNorm is folded around the GEMM, W . LN(x) = rstd (W' x - mu rowsum(W')) + W beta.
+ * wfold: W' = W diag(gamma) as fp16 k-chunk planar [16][2C][8] (K zero-padded to 128); wvec: fp32 rowsum(W')[2C] then (W beta)[2C]
+ * (host/packing.py pack_ln_pw_tc). */
+int gsn_ln_pw_tc(const void *x, const void *hw_pre, int T, int H, int W, int C, int mode, int circular, const void *wfold,
+                 const float *wvec, void *ga, void *gb, void *stream);
 /* g = (dw3x3(a)+a) * (dw3x3(b)+b) (RepConv2 + SimpleGate); wd fp16 [9][2C]; partial (optional) [T][tiles_linear][C]. */
 int gsn_dw_gate(const void *a, const void *b, int T, int H, int W, int C, const void *wd, void *out, float *partial,
                 void *stream);

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -s -k "ln_pw or (gated_cab and deblur1) or (shift_block and deblur1) or K3 or golden" > gpurun_out/lnpw_test.log 2>&1; echo "pytest exit $?" >> gpurun_out/lnpw_test.log
+grep -E "ln_pw|parity-at-size|passed|failed|Error|error|exit" gpurun_out/lnpw_test.log | head -30
+if grep -q "pytest exit 0" gpurun_out/lnpw_test.log; then
+  for tc in 1 0; do
+    GSN_LN_PW_TC=$tc timeout 600 python bench.py --arch gshift_deblur1 --frames 52 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/lnpw_k3_tc$tc.json 2> gpurun_out/lnpw_k3_tc$tc.err
+    python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/lnpw_k3_tc$tc.json")); r=d["roofline"]
+    print("K3 GSN_LN_PW_TC=$tc:", round(d["value"],2), "fps", round(d["ms_per_step"],1), "ms", r["kernel_share_of_step"])
+except Exception as e: print("ERR", e, open("gpurun_out/lnpw_k3_tc$tc.err").read()[-1500:])
+PY
+  done
+fi

@@ -35,6 +35,7 @@ class Engine:
         # CAB1's by the epilogue of the preceding pass B (GsnCabPassB.a1_next).  GSN_LN_FUSE=0 runs the un-fused chain
         # gsn_shift_conv1 -> gsn_ln_planar instead (cross-check in the tests).
         self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
+        self.ln_pw_tc = os.environ.get("GSN_LN_PW_TC", "1") == "1"     # Ours+: LayerNorm + first 1x1 on tcgen05 (0: mma.sync kernel)
         self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
         self.tshard = None             # host/tshard.py TShard: this engine holds only a slice of the clip's frames
         # HFMA2/HMUL2 thread-instructions per pixel of the 16x16-tile pass A (its two depthwise stages: 15.1 k warp-instructions per
@@ -306,8 +307,9 @@ class Engine:
             rp = p + f".body.{3 + k}"
             wfrag = P.pack_group_conv5(sd[rp + ".conv_1.weight"], sd[rp + ".conv_2.weight"])
             w2p = P.planar_chunks(sd[p + f".body.{4 + k}.weight"].flatten(1)).contiguous()      # [C/8][2C][8] fp16
-            self.cache[ck] = self._up((ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p, w1p))
-        ln, wc1, wd, wfrag, fw, w2p, w1p = self.cache[ck]
+            wfold, wvec = P.pack_ln_pw_tc(w1, sd[p + ".norm.weight"], sd[p + ".norm.bias"])
+            self.cache[ck] = self._up((ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p, w1p, wfold, wvec))
+        ln, wc1, wd, wfrag, fw, w2p, w1p, wfold, wvec = self.cache[ck]
         hw_pre = None
         if shift:      # gather folded into conv1's load stage (TMA-staged box), written once, read by the LayerNorm kernel
             hw_pre = self._new(T, H, W, Cc // 2)
@@ -317,9 +319,14 @@ class Engine:
         # LayerNorm + first 1x1 in one kernel (the 1.5C-wide LN input never goes to HBM), a|b halves written separately
         ga, gb = self._new(T, H, W, Cc), self._new(T, H, W, Cc)
         with self._timed("ln_pw", T * H * W):
-            L.check(self.lib.gsn_ln_pw(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
-                                       1 if self.spec.circular else 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
-                                       self._stream()), "ln_pw " + p)
+            if self.ln_pw_tc and Cc == 80:      # TMA + tcgen05 streaming kernel, LayerNorm folded around the GEMM (csrc/ln_pw_tc.cu)
+                L.check(self.lib.gsn_ln_pw_tc(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
+                                              1 if self.spec.circular else 0, wfold.data_ptr(), wvec.data_ptr(), ga.data_ptr(),
+                                              gb.data_ptr(), self._stream()), "ln_pw_tc " + p)
+            else:
+                L.check(self.lib.gsn_ln_pw(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
+                                           1 if self.spec.circular else 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                           self._stream()), "ln_pw " + p)
         del hw_pre
         ntl = self.lib.gsn_cab_tiles_linear(H * W)
         g = self._new(T, H, W, Cc)

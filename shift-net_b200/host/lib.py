@@ -14,7 +14,7 @@ EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in", "gsn_conv_in_nm",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
-    "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
+    "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_ln_pw_tc", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
     "gsn_cab_dense_tiles", "gsn_cab_dense", "gsn_u8_to_clip", "gsn_psnr_sse_blocks", "gsn_psnr_sse", "gsn_ssim_blocks", "gsn_ssim_workspace_bytes", "gsn_ssim",
 ]
 
@@ -98,6 +98,7 @@ def load():
     lib.gsn_ln_planar.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp]
     lib.gsn_shift_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, i, vp, vp]
     lib.gsn_ln_pw.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.gsn_ln_pw_tc.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     lib.gsn_dw_gate.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.gsn_gate2.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.gsn_group_conv5.argtypes = [vp, i, i, i, i, vp, vp, vp, vp]

@@ -144,3 +144,17 @@ def pack_group_conv5(w5, w3):
     v = wm.view(C // 8, 8, 4, 2, 13, 2)            # (group, n, tig, e, kstep, tsel) ; cin = 2*tig + e ; tap = 2*kstep + tsel
     v = v.permute(0, 4, 1, 2, 5, 3).contiguous()   # (group, kstep, n, tig, tsel, e) -> lane = n*4 + tig, regs (b0, b1)
     return v.reshape(-1).half()
+
+
+def pack_ln_pw_tc(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm folded around the first 1x1 of a C=80 gated block for csrc/ln_pw_tc.cu:
+    W . LN(x) = rstd * (W' . x - mu * rowsum(W')) + W . beta with W' = W diag(gamma).
+    w1 (2C, cin) fp32 -> (W' as fp16 k-chunk planar [16 planes][2C][8], K zero-padded to 128 ; fp32 [rowsum of the ROUNDED W' | W . beta])."""
+    w1 = w1.float()
+    n, cin = w1.shape
+    wf = (w1 * gamma.float().view(1, -1)).half()
+    wz = torch.zeros(n, 128, dtype=torch.float16, device=w1.device)
+    wz[:, :cin] = wf
+    wsum = wf.double().sum(1).float()
+    bias = (w1.double() @ beta.double()).float()
+    return planar_chunks(wz.float()).contiguous(), torch.cat((wsum, bias)).contiguous()

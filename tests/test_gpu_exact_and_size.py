@@ -142,6 +142,49 @@ def test_group_conv5_nonuniform_scale():
             assert ((wrong - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() > 0.05
 
 
+@pytest.mark.parametrize("mode_name", ["cab1", "cab2_fwd", "cab2_rev"])
+def test_ln_pw_tcgen05_vs_mma_sync_and_torch(mode_name):
+    """gsn_ln_pw_tc (TMA + tcgen05, LayerNorm folded around the GEMM) against gsn_ln_pw (mma.sync, LayerNorm in shared memory) and
+    against torch fp32: W . LayerNorm([rolled stream | conv1(shifted half)]) for C = 80, clamped roll, ragged pixel count."""
+    lib = L.load()
+    mode = {"cab1": L.MODE_CAB1, "cab2_fwd": L.MODE_CAB2_FWD, "cab2_rev": L.MODE_CAB2_REV}[mode_name]
+    g = torch.Generator().manual_seed(31)
+    T, Cc, H, W = 3, 80, 37, 45
+    cin = Cc if mode == L.MODE_CAB1 else Cc + Cc // 2
+    x = 0.5 * torch.randn(T, Cc, H, W, generator=g) + 0.3
+    hwp = 0.5 * torch.randn(T, Cc // 2, H, W, generator=g)
+    w1 = torch.randn(2 * Cc, cin, generator=g) / cin ** 0.5
+    gamma, beta = 1 + 0.1 * torch.randn(cin, generator=g), 0.1 * torch.randn(cin, generator=g)
+    xd, hd = nhwc16(x), nhwc16(hwp)
+    wfold, wvec = (t.to(DEV) for t in P.pack_ln_pw_tc(w1, gamma, beta))
+    kpad = (cin + 15) // 16 * 16
+    w1z = torch.zeros(2 * Cc, kpad)
+    w1z[:, :cin] = w1
+    w1p = P.planar_chunks(w1z).contiguous().to(DEV)
+    ln = torch.cat((gamma, beta)).to(DEV)
+    outs = []
+    for tc in (True, False):
+        ga = torch.empty(T, H, W, Cc, dtype=torch.float16, device=DEV)
+        gb = torch.empty_like(ga)
+        hp = hd.data_ptr() if mode != L.MODE_CAB1 else None
+        if tc:
+            L.check(lib.gsn_ln_pw_tc(xd.data_ptr(), hp, T, H, W, Cc, mode, 0, wfold.data_ptr(), wvec.data_ptr(), ga.data_ptr(), gb.data_ptr(), _stream()), "ln_pw_tc")
+        else:
+            L.check(lib.gsn_ln_pw(xd.data_ptr(), hp, T, H, W, Cc, mode, 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(), _stream()), "ln_pw")
+        torch.cuda.synchronize()
+        outs.append(torch.cat((ga, gb), -1).permute(0, 3, 1, 2).float().cpu())
+    xq, hq = x.half().float(), hwp.half().float()
+    if mode == L.MODE_CAB1:
+        a = xq
+    else:
+        a = torch.cat((O.temporal_roll(xq, mode == L.MODE_CAB2_REV, False)[0], hq), 1)
+    ref = F.conv2d(O.layer_norm2d(a, gamma, beta), w1.view(2 * Cc, cin, 1, 1))
+    for name, o in zip(("tcgen05", "mma.sync"), outs):
+        r = ((o - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        print(f"[parity] ln_pw {mode_name} {name}: rel_rms={r:.2e}")
+        assert torch.isfinite(o).all() and r < 2e-3, (name, r)
+
+
 def test_conv_in_noise_map_strided_vs_cat():
     """gsn_conv_in_nm reads the noise map through its strides (expand()ed (1,T,1,H,W) view of one scalar, as
     inference/test_denoise_small.py:162 passes it) -- same result as the conv over torch.cat((x, noise_map), 1)."""

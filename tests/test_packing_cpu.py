@@ -114,3 +114,23 @@ def test_fold_pack_has_the_mid_attention_for_denoise_only():
     sd2, _ = gio.synthetic_checkpoint("gshift_deblur2")
     d2 = P.pack_cab_fold(sd2, p, 0)
     assert d2["bias3"] is None and "mid_du0" not in d2 and d2["w3"].shape == (64, 64)
+
+
+@pytest.mark.parametrize("cin", [80, 120])
+def test_layernorm_folding_around_the_first_1x1(cin):
+    """pack_ln_pw_tc (csrc/ln_pw_tc.cu): rstd * (W' x - mu rowsum(W')) + W beta with the packed (fp16-rounded) W' reproduces
+    W . LayerNorm(x) (gshift_deblur1.py:19-28,209,250) -- also for pixels whose mean is large against their spread, where the mean
+    term only cancels because rowsum is taken over the ROUNDED weights."""
+    g = torch.Generator().manual_seed(cin)
+    w1 = torch.randn(160, cin, generator=g) / cin ** 0.5
+    gamma, beta = 1 + 0.1 * torch.randn(cin, generator=g), 0.1 * torch.randn(cin, generator=g)
+    wfold, wvec = P.pack_ln_pw_tc(w1, gamma, beta)
+    assert wfold.shape == (16, 160, 8) and wfold.dtype == torch.float16 and wvec.shape == (320,)
+    wp = wfold.float().permute(1, 0, 2).reshape(160, 128)
+    assert wp[:, cin:].abs().max() == 0
+    x = (torch.randn(64, cin, generator=g) * torch.rand(64, 1, generator=g) + 3.0 * torch.randn(64, 1, generator=g)).half().float()
+    mu = x.mean(1, keepdim=True)
+    rstd = ((x - mu).pow(2).mean(1, keepdim=True) + 1e-6).rsqrt()
+    got = rstd * (x @ wp[:, :cin].t() - mu * wvec[:160]) + wvec[160:]
+    ref = (((x - mu) * rstd) * gamma + beta) @ w1.t()
+    assert ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() < 1e-3
