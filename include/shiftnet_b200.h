@@ -69,6 +69,13 @@ typedef struct {
 int gsn_conv_tiles(int Hout, int Wout);
 int gsn_conv_mma(const GsnConvDesc *d, void *stream);
 
+/* The same conv for the wide CAB bodies of Ours+ (3x3, stride 1, pad 1, one source with 40 or 48 stored channels, 40 or 48 stored
+ * output channels, optional bias / PReLU / chan_partial; no residual, no shuffle) as an implicit GEMM on tcgen05: the 9 taps are
+ * descriptor offsets into one TMA-landed k-chunk planar tile.  wpack: fp16 [9][6][48][8] (host/packing.py pack_conv3x3_tc), bias: 48
+ * floats or NULL, chan_partial: [T][gsn_conv3x3_tc_tiles(H,W)][cout_p]. */
+int gsn_conv3x3_tc_tiles(int H, int W);
+int gsn_conv3x3_tc(const GsnConvDesc *d, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused body of the dense channel-attention block: r = conv3x3(PReLU(conv3x3(x))) in ONE kernel (the intermediate
  * stays in shared memory) plus the per-tile channel sums of r for the CALayer pooling.  Replaces the two nn.Conv2d

@@ -35,6 +35,7 @@ class Engine:
         # CAB1's by the epilogue of the preceding pass B (GsnCabPassB.a1_next).  GSN_LN_FUSE=0 runs the un-fused chain
         # gsn_shift_conv1 -> gsn_ln_planar instead (cross-check in the tests).
         self.ln_fuse = os.environ.get("GSN_LN_FUSE", "1") == "1"
+        self.conv_tc = os.environ.get("GSN_CONV_TC", "1") == "1"       # Ours+: 40/48-channel CAB convs on tcgen05 (0: mma.sync conv_mma)
         self.ln_pw_tc = os.environ.get("GSN_LN_PW_TC", "1") == "1"     # Ours+: LayerNorm + first 1x1 on tcgen05 (0: mma.sync kernel)
         self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
         self.tshard = None             # host/tshard.py TShard: this engine holds only a slice of the clip's frames
@@ -160,6 +161,31 @@ class Engine:
             L.check(self.lib.gsn_conv_mma(C.byref(d), self._stream()), "conv_mma " + key)
         return (dst, partial) if want_sums else dst
 
+    def conv3x3_tc(self, key, x, c, prelu_key=None, want_sums=False):
+        """Same-width 3x3 / stride 1 conv of a 40- or 48-channel tensor on the tcgen05 implicit-GEMM kernel."""
+        T, H, W, cp = x.shape
+        ck = ("conv3tc", key)
+        if ck not in self.cache:
+            b = self.sd.get(key + ".bias")
+            self.cache[ck] = self._up((P.pack_conv3x3_tc(self.sd[key + ".weight"]), P.pack_bias(b, 48) if b is not None else None))
+        wp, bias = self.cache[ck]
+        dst = self._new(T, H, W, cp)
+        partial = self._new(T, self.lib.gsn_conv3x3_tc_tiles(H, W), cp, dtype=torch.float32) if want_sums else None
+        d = L.ConvDesc()
+        d.T, d.Hin, d.Win, d.Hout, d.Wout = T, H, W, H, W
+        d.n_src = 1
+        d.src[0], d.src_c[0] = x.data_ptr(), cp
+        d.cin_p, d.cout_p, d.ks, d.stride, d.pad = 48, cp, 3, 1, 1
+        d.wpack = wp.data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.has_prelu = 1 if prelu_key else 0
+        d.prelu_slope = self._slope(prelu_key) if prelu_key else 0.0
+        d.chan_partial = partial.data_ptr() if partial is not None else None
+        d.dst = dst.data_ptr()
+        with self._timed(f"conv3x3_tc[{cp} {H}x{W}]" if self.timeline_detail else "conv3x3_tc", T * H * W):
+            L.check(self.lib.gsn_conv3x3_tc(C.byref(d), self._stream()), "conv3x3_tc " + key)
+        return (dst, partial) if want_sums else dst
+
     # ------------------------------------------------------------------ CAB (dense 3x3 + channel attention)
     def cab_body_fused(self, p, x, c):
         """conv3x3 -> PReLU -> conv3x3 of CAB.body (gshift_deblur2.py:146-150) in one kernel (csrc/cab_dense.cu)."""
@@ -187,6 +213,9 @@ class Engine:
         """gshift_deblur2.py:143-158.  ``extra`` is an optional tensor added to the result (stage shortcuts)."""
         if self.cab_fused and x.shape[3] in (16, 24):
             r2, partial = self.cab_body_fused(p, x, c)
+        elif self.conv_tc and x.shape[3] in (40, 48):      # Ours+ TFR_UNet levels 2 / 3: both 3x3 convs on tcgen05 (csrc/conv3x3_tc.cu)
+            r1 = self.conv3x3_tc(p + ".body.0", x, c, prelu_key=p + ".body.1.weight")
+            r2, partial = self.conv3x3_tc(p + ".body.2", r1, c, want_sums=True)
         else:
             r1 = self.conv(p + ".body.0", [x], [c], c, prelu_key=p + ".body.1.weight")
             r2, partial = self.conv(p + ".body.2", [r1], [c], c, want_sums=True)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libshiftnet_b200.so")
 
 EXPORTS = [
-    "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv_in", "gsn_conv_in_nm",
+    "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv3x3_tc_tiles", "gsn_conv3x3_tc", "gsn_conv_in", "gsn_conv_in_nm",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
     "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
     "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_ln_pw_tc", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
@@ -78,6 +78,8 @@ def load():
     lib.gsn_launch_count.restype = C.c_ulonglong
     lib.gsn_conv_tiles.argtypes = [i, i]
     lib.gsn_conv_mma.argtypes = [C.POINTER(ConvDesc), vp]
+    lib.gsn_conv3x3_tc_tiles.argtypes = [i, i]
+    lib.gsn_conv3x3_tc.argtypes = [C.POINTER(ConvDesc), vp]
     lib.gsn_conv_in.argtypes = [vp, i, i, i, i, i, vp, vp, i, vp, vp]
     lib.gsn_conv_in_nm.argtypes = [vp, i, i, i, i, i, vp, ll, ll, ll, vp, vp, i, vp, vp]
     lib.gsn_conv_out.argtypes = [vp, i, i, vp, vp, i, i, i, i, i, vp, vp]

@@ -158,3 +158,14 @@ def pack_ln_pw_tc(w1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
     wsum = wf.double().sum(1).float()
     bias = (w1.double() @ beta.double()).float()
     return planar_chunks(wz.float()).contiguous(), torch.cat((wsum, bias)).contiguous()
+
+
+def pack_conv3x3_tc(w: torch.Tensor) -> torch.Tensor:
+    """Dense 3x3 conv weight (cout <= 48, cin <= 48, 3, 3) -> fp16 [tap = ky*3+kx][6 k-chunks][48 rows (n)][8] for csrc/conv3x3_tc.cu:
+    per (tap, k-step) the no-swizzle K-major UMMA B operand (N = 48 rows, two 8-channel chunks); padding rows / channels are zero."""
+    w = w.float()
+    cout, cin, k, _ = w.shape
+    assert k == 3 and cout <= 48 and cin <= 48
+    wz = torch.zeros(48, 48, 9, device=w.device)
+    wz[:cout, :cin] = w.reshape(cout, cin, 9)
+    return wz.view(48, 6, 8, 9).permute(3, 1, 0, 2).contiguous().half()

@@ -185,6 +185,46 @@ def test_ln_pw_tcgen05_vs_mma_sync_and_torch(mode_name):
         assert torch.isfinite(o).all() and r < 2e-3, (name, r)
 
 
+@pytest.mark.parametrize("case", [(36, 40, True, False), (48, 48, False, True), (36, 40, False, True)], ids=["c36_prelu_bias", "c48_sums", "c36_sums"])
+def test_conv3x3_tcgen05_vs_torch_and_mma_sync(case):
+    """gsn_conv3x3_tc (implicit GEMM on tcgen05, taps as descriptor offsets) against torch fp32 and against gsn_conv_mma, on ragged sizes
+    (partial tiles in x and y, more tiles than SMs), with bias + PReLU and with the per-tile channel sums."""
+    c, cp, prelu, sums = case
+    sd, spec = gio.synthetic_checkpoint("gshift_deblur1")
+    eng = gio.pkg("host.engine").Engine(spec, {}, DEV)
+    g = torch.Generator().manual_seed(c)
+    for T, H, W in ((2, 37, 45), (3, 90, 160), (1, 5, 7)):
+        x = torch.randn(T, c, H, W, generator=g)
+        w = torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5
+        key = f"testc3.{c}.{H}"
+        eng.sd[key + ".weight"] = w
+        b = None
+        if prelu:
+            b = 0.1 * torch.randn(c, generator=g)
+            eng.sd[key + ".bias"] = b
+            eng.sd[key + ".slope"] = torch.tensor([0.2])
+        xd = torch.zeros(T, H, W, cp, dtype=torch.float16, device=DEV)
+        xd[..., :c] = x.permute(0, 2, 3, 1).to(DEV).half()
+        ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+        if prelu:
+            ref = F.prelu(ref, torch.tensor([0.2]))
+        res = eng.conv3x3_tc(key, xd, c, prelu_key=key + ".slope" if prelu else None, want_sums=sums)
+        out, partial = res if sums else (res, None)
+        ref2 = eng.conv(key, [xd], [c], c, prelu_key=key + ".slope" if prelu else None)
+        torch.cuda.synchronize()
+        got = out[..., :c].permute(0, 3, 1, 2).float().cpu()
+        r = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        r2 = ((got - ref2[..., :c].permute(0, 3, 1, 2).float().cpu()).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        print(f"[parity] conv3x3_tc c={c} {T}x{H}x{W}: vs torch {r:.2e} ; vs conv_mma {r2:.2e}")
+        assert torch.isfinite(out).all() and r < 2e-3 and r2 < 1e-3
+        if cp > c:
+            assert out[..., c:].abs().max().item() == 0.0, "padding channels must stay zero"
+        if sums:
+            s_got = partial.sum(1)[:, :c].cpu()
+            s_ref = out[..., :c].float().sum((1, 2)).cpu()
+            assert torch.allclose(s_got, s_ref, rtol=2e-3, atol=2e-2 * (H * W) ** 0.5), (s_got - s_ref).abs().max()
+
+
 def test_conv_in_noise_map_strided_vs_cat():
     """gsn_conv_in_nm reads the noise map through its strides (expand()ed (1,T,1,H,W) view of one scalar, as
     inference/test_denoise_small.py:162 passes it) -- same result as the conv over torch.cat((x, noise_map), 1)."""
