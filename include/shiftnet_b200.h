@@ -222,6 +222,10 @@ int gsn_cab_tiles_linear(long long hw);
 int gsn_cab_pass_a2(const void *u, const void *w2eff, void *z, float *chan_partial, int T, int H, int W, int C,
                     int per_frame_weights /* 1: w2eff is [T][..] from gsn_cab_fold_mid; 0: one [C/8][2C][8] weight */, void *stream);
 
+/* The same stage for C = 80 on TMA + tcgen05 (one weight for all frames): w2half = 0.5 * W2 as fp16 k-chunk planar [C/8][2C][8]
+ * (a * sigmoid(b) = (a/2) tanh(b/2) + a/2); chan_partial [T][gsn_cab_tiles_linear(H*W)][C]. */
+int gsn_pw_gate_tc(const void *u, const void *w2half, void *z, float *chan_partial, int T, int H, int W, int C, void *stream);
+
 /* fold: weff[t] = diag(beta) W3 diag(s_t) as fp16 [T][C/8][C][8] (k-chunk planar), s_t from CALayer2
  * (d2:72-89,238-239,257).  w_du0 [cr][C], w_du2 [C][cr], w3 [C][C], beta [C], bias3 [C] or NULL (fp32).
  * beff [T][C] fp32 = beta*bias3 (zeros if bias3 == NULL). */

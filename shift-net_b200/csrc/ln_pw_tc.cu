@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) ln_pw_tc_kernel(const __grid_co
 }
 
 // 3-D fp16 tensor map over a (T, HW, C) pixel-major tensor with an (8 channels, 128 pixels, 1) box: one k-chunk plane of a tile
-static bool encode_tmap_chunk(CUtensorMap *tm, const void *base, int C, long long hw, int T) {
+bool encode_tmap_chunk128(CUtensorMap *tm, const void *base, int C, long long hw, int T) {
   typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -228,7 +228,7 @@ extern "C" int gsn_ln_pw_tc(const void *x, const void *hw_pre, int T, int H, int
   CUtensorMap tm_x, tm_hw;
   memset(&tm_x, 0, sizeof(tm_x));
   memset(&tm_hw, 0, sizeof(tm_hw));
-  if (!encode_tmap_chunk(&tm_x, x, C, hw, T) || (hw_pre && !encode_tmap_chunk(&tm_hw, hw_pre, C / 2, hw, T))) {
+  if (!encode_tmap_chunk128(&tm_x, x, C, hw, T) || (hw_pre && !encode_tmap_chunk128(&tm_hw, hw_pre, C / 2, hw, T))) {
     set_error("ln_pw_tc: cuTensorMapEncodeTiled failed (H*W=%lld T=%d)", hw, T);
     return GSN_E_CUDA;
   }

@@ -337,8 +337,9 @@ class Engine:
             wfrag = P.pack_group_conv5(sd[rp + ".conv_1.weight"], sd[rp + ".conv_2.weight"])
             w2p = P.planar_chunks(sd[p + f".body.{4 + k}.weight"].flatten(1)).contiguous()      # [C/8][2C][8] fp16
             wfold, wvec = P.pack_ln_pw_tc(w1, sd[p + ".norm.weight"], sd[p + ".norm.bias"])
-            self.cache[ck] = self._up((ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p, w1p, wfold, wvec))
-        ln, wc1, wd, wfrag, fw, w2p, w1p, wfold, wvec = self.cache[ck]
+            w2h = P.planar_chunks(0.5 * sd[p + f".body.{4 + k}.weight"].float().flatten(1)).contiguous()   # half scale: exact in fp16
+            self.cache[ck] = self._up((ln, wc1, wd, wfrag, P.pack_cab_fold(sd, p, k), w2p, w1p, wfold, wvec, w2h))
+        ln, wc1, wd, wfrag, fw, w2p, w1p, wfold, wvec, w2h = self.cache[ck]
         hw_pre = None
         if shift:      # gather folded into conv1's load stage (TMA-staged box), written once, read by the LayerNorm kernel
             hw_pre = self._new(T, H, W, Cc // 2)
@@ -377,8 +378,12 @@ class Engine:
         z = self._new(T, H, W, Cc)
         partial = self._new(T, ntl, Cc, dtype=torch.float32)
         with self._timed("cab_pass_a2", T * H * W):
-            L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2p.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 0,
-                                             self._stream()), "cab_pass_a2")
+            if self.ln_pw_tc and Cc == 80:      # TMA + tcgen05 streaming kernel (csrc/pw_gate_tc.cu)
+                L.check(self.lib.gsn_pw_gate_tc(u.data_ptr(), w2h.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc,
+                                                self._stream()), "pw_gate_tc")
+            else:
+                L.check(self.lib.gsn_cab_pass_a2(u.data_ptr(), w2p.data_ptr(), z.data_ptr(), partial.data_ptr(), T, H, W, Cc, 0,
+                                                 self._stream()), "cab_pass_a2")
         del u
         return self._fold_and_pass_b(p, x, z, partial, ntl, fw, mode)
 

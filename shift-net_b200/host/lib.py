@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libshiftnet_b200.so")
 EXPORTS = [
     "gsn_version", "gsn_last_error", "gsn_launch_count", "gsn_conv_tiles", "gsn_conv_mma", "gsn_conv3x3_tc_tiles", "gsn_conv3x3_tc", "gsn_conv_in", "gsn_conv_in_nm",
     "gsn_conv_out", "gsn_ca_scale", "gsn_scale_residual", "gsn_upsample2x_add", "gsn_add", "gsn_cab_tiles",
-    "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2",
+    "gsn_cab_pass_a", "gsn_cab_pass_a_tiles", "gsn_cab_fold", "gsn_cab_pass_b", "gsn_cab_fold_mid", "gsn_cab_tiles_linear", "gsn_cab_pass_a2", "gsn_pw_gate_tc",
     "gsn_shift_conv1", "gsn_shift_conv1_ln", "gsn_ln_planar", "gsn_shift_ln", "gsn_ln_pw", "gsn_ln_pw_tc", "gsn_dw_gate", "gsn_gate2", "gsn_group_conv5", "gsn_roll_copy",
     "gsn_cab_dense_tiles", "gsn_cab_dense", "gsn_u8_to_clip", "gsn_psnr_sse_blocks", "gsn_psnr_sse", "gsn_ssim_blocks", "gsn_ssim_workspace_bytes", "gsn_ssim",
 ]
@@ -95,6 +95,7 @@ def load():
     lib.gsn_cab_fold_mid.argtypes = [vp, i, f, vp, vp, i, vp, i, i, vp, vp]
     lib.gsn_cab_tiles_linear.argtypes = [ll]
     lib.gsn_cab_pass_a2.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.gsn_pw_gate_tc.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.gsn_shift_conv1.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp]
     lib.gsn_shift_conv1_ln.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp]
     lib.gsn_ln_planar.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, vp]

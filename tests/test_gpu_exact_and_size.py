@@ -225,6 +225,38 @@ def test_conv3x3_tcgen05_vs_torch_and_mma_sync(case):
             assert torch.allclose(s_got, s_ref, rtol=2e-3, atol=2e-2 * (H * W) ** 0.5), (s_got - s_ref).abs().max()
 
 
+def test_pw_gate_tcgen05_vs_mma_sync_and_torch():
+    """gsn_pw_gate_tc (second 1x1 + SimpleGate2 + channel sums on TMA + tcgen05, half-scale weights + tanh) against gsn_cab_pass_a2
+    (mma.sync) and torch fp32, C = 80, pixel counts that are not multiples of the 128-pixel tile."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(41)
+    Cc = 80
+    for T, H, W in ((2, 37, 45), (3, 16, 24), (1, 90, 160)):
+        u = 0.7 * torch.randn(T, Cc, H, W, generator=g)
+        w2 = torch.randn(2 * Cc, Cc, generator=g) / Cc ** 0.5
+        ud = nhwc16(u)
+        w2p = P.planar_chunks(w2).contiguous().to(DEV)
+        w2h = P.planar_chunks(0.5 * w2).contiguous().to(DEV)
+        ntl = lib.gsn_cab_tiles_linear(H * W)
+        outs = []
+        for tc in (True, False):
+            z = torch.empty(T, H, W, Cc, dtype=torch.float16, device=DEV)
+            part = torch.empty(T, ntl, Cc, dtype=torch.float32, device=DEV)
+            if tc:
+                L.check(lib.gsn_pw_gate_tc(ud.data_ptr(), w2h.data_ptr(), z.data_ptr(), part.data_ptr(), T, H, W, Cc, _stream()), "pw_gate_tc")
+            else:
+                L.check(lib.gsn_cab_pass_a2(ud.data_ptr(), w2p.data_ptr(), z.data_ptr(), part.data_ptr(), T, H, W, Cc, 0, _stream()), "cab_pass_a2")
+            torch.cuda.synchronize()
+            outs.append((z.permute(0, 3, 1, 2).float().cpu(), part.sum(1).cpu()))
+        v = F.conv2d(u.half().float(), w2.half().float().view(2 * Cc, Cc, 1, 1))
+        ref = v[:, :Cc] * torch.sigmoid(v[:, Cc:])
+        for name, (o, sm) in zip(("tcgen05", "mma.sync"), outs):
+            r = ((o - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+            print(f"[parity] pw_gate {T}x{H}x{W} {name}: rel_rms={r:.2e}")
+            assert torch.isfinite(o).all() and r < 2e-3, (name, r)
+            assert torch.allclose(sm, o.sum((2, 3)), rtol=2e-3, atol=2e-2 * (H * W) ** 0.5), (name, (sm - o.sum((2, 3))).abs().max())
+
+
 def test_conv_in_noise_map_strided_vs_cat():
     """gsn_conv_in_nm reads the noise map through its strides (expand()ed (1,T,1,H,W) view of one scalar, as
     inference/test_denoise_small.py:162 passes it) -- same result as the conv over torch.cat((x, noise_map), 1)."""
