@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(256, 3) cab_pass_a2_kernel(const __half *__res
 int cab_pass_a_pre_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_pre.cu
 int cab_pass_a_stream_dispatch(const GsnCabPassA &d, cudaStream_t st); // cab_pass_a_stream.cu
 int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b_tc.cu
+int cab_pass_b80_tc_dispatch(const GsnCabPassB &d, cudaStream_t st);  // cab_pass_b80_tc.cu
 bool pass_a_stream_enabled();
 int pass_a_stream_tiles(int T, int H, int W);
 // Two pass-A kernels serve C = 64: the 16x16-tile kernel (cab_pass_a_pre.cu, default) and the row-streaming warp-specialised
@@ -419,9 +420,10 @@ extern "C" int gsn_cab_pass_b(const GsnCabPassB *dp, void *stream) {
   GSN_REQUIRE(d.mode >= GSN_MODE_CAB1 && d.mode <= GSN_MODE_CAB2_REV, "cab_pass_b: mode=%d", d.mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long hw = (long long)d.H * d.W;
-  // C = 64: the TMA / tcgen05 streaming kernel (cab_pass_b_tc.cu); GSN_PASS_B_TC=0 keeps the mma.sync kernel below
+  // the TMA / tcgen05 streaming kernels (cab_pass_b_tc.cu for C = 64, cab_pass_b80_tc.cu for C = 80); GSN_PASS_B_TC=0 keeps the mma.sync kernel below
   static const bool want_tc = [] { const char *e = getenv("GSN_PASS_B_TC"); return !(e && e[0] == '0'); }();
   if (d.C == 64 && want_tc) return cab_pass_b_tc_dispatch(d, st);
+  if (d.C == 80 && want_tc) return cab_pass_b80_tc_dispatch(d, st);     // planar-chunk variant for the Ours+ width (cab_pass_b80_tc.cu)
   dim3 grid((unsigned)((hw + 127) / 128), d.T);
   if (d.C == 64) {
     constexpr int smem = 2 * 8 * 129 * 16 + 8 * 64 * 16;
