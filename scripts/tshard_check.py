@@ -23,11 +23,17 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 T, H, W = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 256, 448)))
-sd, spec = gio.synthetic_checkpoint("gshift_deblur2")
-net = importlib.import_module("basicsr.models.archs.gshift_deblur2").GShiftNet(future_frames=2, past_frames=2)
+ARCH = sys.argv[4] if len(sys.argv) > 4 else "gshift_deblur2"
+sd, spec = gio.synthetic_checkpoint(ARCH)
+net = importlib.import_module("basicsr.models.archs." + ARCH).GShiftNet(future_frames=2, past_frames=2)
 net.load_state_dict(sd)
 net = net.half().to(dev).eval()
-_, x = gio.pkg("host.synth").synthetic_clip(T, H, W)
+nm = None
+if spec.denoise:
+    _, x, nm = gio.pkg("host.synth").synthetic_clip(T, H, W, denoise_sigma=30)
+    nm = nm.half().to(dev)
+else:
+    _, x = gio.pkg("host.synth").synthetic_clip(T, H, W)
 x = x.half().to(dev)
 ts = gio.pkg("host.tshard").TShard(rank, world, T)
 ts.time_exchanges = True
@@ -37,7 +43,7 @@ for it in range(3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out_local = net.forward_tsharded(x[:, ts.a:ts.b].contiguous(), ts)
+    out_local = net.forward_tsharded(x[:, ts.a:ts.b].contiguous(), ts, None if nm is None else nm[:, ts.a:ts.b].contiguous())
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
@@ -57,9 +63,9 @@ if world > 1:
 else:
     full = out_local
 if rank == 0:
-    ref = net(x)
+    ref = net(x, nm) if nm is not None else net(x)
     ok = tuple(full.shape) == tuple(ref.shape) and torch.equal(full, ref)
-    print(f"[tshard] T={T} {H}x{W} on {world} rank(s): gathered {tuple(full.shape)} vs single-GPU forward: "
+    print(f"[tshard] {ARCH} T={T} {H}x{W} on {world} rank(s): gathered {tuple(full.shape)} vs single-GPU forward: "
           f"{'BIT-EXACT' if ok else 'MISMATCH max|diff| = %.3e' % (full.float() - ref.float()).abs().max().item()}", flush=True)
 if world > 1:
     dist.barrier()

@@ -39,6 +39,7 @@ class Engine:
         self.ln_pw_tc = os.environ.get("GSN_LN_PW_TC", "1") == "1"     # Ours+: LayerNorm + first 1x1 on tcgen05 (0: mma.sync kernel)
         self.pass_a_stream = False     # True: route every C=64 deblur pass A to the row-streaming kernel (cab_pass_a_stream.cu)
         self.tshard = None             # host/tshard.py TShard: this engine holds only a slice of the clip's frames
+        self._circ_override = None
         # HFMA2/HMUL2 thread-instructions per pixel of the 16x16-tile pass A (its two depthwise stages: 15.1 k warp-instructions per
         # 256-pixel tile incl. the halo recompute): bench.py reports the kernel against the FMA pipe with it
         self.pass_a_hfma2_per_pixel = 15.1e3 * 32 / 256
@@ -95,6 +96,12 @@ class Engine:
         if isinstance(t, (tuple, list)):
             return tuple(self._up(v) for v in t)
         return t.contiguous().to(self.dev)
+
+    def _circ(self):
+        """Temporal roll wraps around the frames of the tensor at hand: the arch's rule (gshift_deblur2.py:504-505 wraps, the other three
+        nets clamp), unless a T-sharded CAB2 step overrides it (a halo frame behind the rank's frames is reached by wrapping)."""
+        ov = self._circ_override
+        return (1 if self.spec.circular else 0) if ov is None else ov
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -306,7 +313,7 @@ class Engine:
         else:
             out = self._new(T, H, W, Cc)
         b = L.CabPassB()
-        b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
+        b.T, b.H, b.W, b.C, b.mode, b.circular = T, H, W, Cc, mode, self._circ()
         b.x, b.z, b.weff, b.beff, b.out = x.data_ptr(), z.data_ptr(), weff.data_ptr(), beff.data_ptr(), out.data_ptr()
         self._a1_next = None
         if next_p is not None:      # the LayerNorm of the block that consumes `out` rides on this kernel's epilogue
@@ -344,18 +351,18 @@ class Engine:
         if shift:      # gather folded into conv1's load stage (TMA-staged box), written once, read by the LayerNorm kernel
             hw_pre = self._new(T, H, W, Cc // 2)
             with self._timed("shift_conv1", T * H * W):
-                L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, 1 if self.spec.circular else 0, wc1.data_ptr(),
+                L.check(self.lib.gsn_shift_conv1(x.data_ptr(), T, H, W, Cc, mode, self._circ(), wc1.data_ptr(),
                                                  hw_pre.data_ptr(), self._stream()), "shift_conv1 " + p)
         # LayerNorm + first 1x1 in one kernel (the 1.5C-wide LN input never goes to HBM), a|b halves written separately
         ga, gb = self._new(T, H, W, Cc), self._new(T, H, W, Cc)
         with self._timed("ln_pw", T * H * W):
             if self.ln_pw_tc and Cc == 80:      # TMA + tcgen05 streaming kernel, LayerNorm folded around the GEMM (csrc/ln_pw_tc.cu)
                 L.check(self.lib.gsn_ln_pw_tc(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
-                                              1 if self.spec.circular else 0, wfold.data_ptr(), wvec.data_ptr(), ga.data_ptr(),
+                                              self._circ(), wfold.data_ptr(), wvec.data_ptr(), ga.data_ptr(),
                                               gb.data_ptr(), self._stream()), "ln_pw_tc " + p)
             else:
                 L.check(self.lib.gsn_ln_pw(x.data_ptr(), hw_pre.data_ptr() if hw_pre is not None else None, T, H, W, Cc, mode,
-                                           1 if self.spec.circular else 0, ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                           self._circ(), ln.data_ptr(), w1p.data_ptr(), ga.data_ptr(), gb.data_ptr(),
                                            self._stream()), "ln_pw " + p)
         del hw_pre
         ntl = self.lib.gsn_cab_tiles_linear(H * W)
@@ -414,7 +421,7 @@ class Engine:
         z = self._new(T, H, W, Cc)
         partial = self._new(T, ntiles, Cc, dtype=torch.float32)
         a = L.CabPassA()
-        a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, 1 if self.spec.circular else 0
+        a.T, a.H, a.W, a.C, a.mode, a.circular = T, H, W, Cc, mode, self._circ()
         a.x, a.wblob, a.z, a.chan_partial = x.data_ptr(), blob.data_ptr(), z.data_ptr(), partial.data_ptr()
         a.mid_ca = 1 if self.spec.denoise else 0
         if shift and self.ln_fuse:
@@ -475,14 +482,22 @@ class Engine:
             rev = bool(i & 1)
             if ts is not None:
                 # this rank's n frames + the neighbour's boundary frame behind them (host/tshard.py): the kernels' circular indexing
-                # over n+1 frames then finds frame 0's predecessor / frame n-1's successor at index n
+                # over n+1 frames then finds frame 0's predecessor / frame n-1's successor at index n.  For the nets whose roll CLAMPS
+                # at the ends of the clip, the rank that holds that end runs the step on its n frames with the clamped rule (it still
+                # serves its other neighbour in the exchange).
                 n = x.shape[0]
+                use_halo = ts.needs_halo(rev, self.spec.circular)
                 full = getattr(x, "_gsn_full", None)
                 if full is None or full.shape[0] != n + 1:
                     full = self._new(n + 1, *x.shape[1:])
                     full[:n].copy_(x)
-                ts.halo_into(full, n, rev)
-                y = self.gated_cab(q + ".0", full, L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
+                ts.halo_into(full, n, rev, circular=self.spec.circular)
+                self._circ_override = 1 if use_halo else 0
+                try:
+                    y = self.gated_cab(q + ".0", full if use_halo else full[:n], L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD,
+                                       next_p=(q + ".1") if fuse else None)
+                finally:
+                    self._circ_override = None
                 a1 = self._a1_next[:n] if (fuse and self._a1_next is not None) else None   # planar operand is frame-major: prefix view
                 x = self.gated_cab(q + ".1", y[:n], L.MODE_CAB1, a1_pre=a1)
                 continue
@@ -589,8 +604,8 @@ class Engine:
             raise ValueError(f"H and W must be multiples of {m} for {sp.name} (got {H}x{W}); the reference scripts crop/pad to that")
         ts = self.tshard
         if ts is not None:
-            if not sp.circular or sp.plus or sp.denoise:
-                raise ValueError("T-sharded mode needs a net whose temporal roll wraps around the clip (gshift_deblur2)")
+            if sp.plus and sp.denoise:
+                raise ValueError("T-sharded mode does not cover gshift_denoise1 (its Shift_CABs roll outside the shift blocks)")
             if T != ts.n_local:
                 raise ValueError(f"T-sharded mode: this rank owns {ts.n_local} frames, got {T}")
             lo, hi = ts.local_output_range(past, future)

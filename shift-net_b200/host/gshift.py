@@ -87,8 +87,9 @@ class GShiftNetB200(nn.Module):
 
 
     @torch.no_grad()
-    def forward_tsharded(self, x_local, tshard):
-        """One slice of a T-sharded clip (host/tshard.py): x_local (1, n_local, 3, H, W) are the frames this rank owns; returns the
+    def forward_tsharded(self, x_local, tshard, noise_map=None):
+        """One slice of a T-sharded clip (host/tshard.py): x_local (1, n_local, 3, H, W) are the frames this rank owns (noise_map
+        (1, n_local, 1, H, W) for the denoise nets); returns the
         restored frames among them (the clip's context frames are cropped on the ranks that hold them).  Launches eagerly: the
         halo exchanges are NCCL point-to-point operations between the kernels."""
         if not x_local.is_cuda:
@@ -98,7 +99,7 @@ class GShiftNetB200(nn.Module):
         eng.tshard = tshard
         try:
             l0 = lib.gsn_launch_count()
-            out = eng.forward(x_local, None, past=self.num_fb, future=self.num_ff)
+            out = eng.forward(x_local, noise_map, past=self.num_fb, future=self.num_ff)
             self.kernel_launches += lib.gsn_launch_count() - l0
         finally:
             eng.tshard = None

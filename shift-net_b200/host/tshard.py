@@ -5,8 +5,9 @@ Everything in GShiftNet.forward is per-frame except the half-channel temporal ro
 (channel_shift, gshift_deblur2.py:499-519): frame t reads C/2 channels of frame t-1 (forward pairs) or t+1 (reverse pairs).
 Each rank therefore needs, before every CAB2, ONE boundary frame's half of the channels from its ring neighbour: the halo
 exchange below (NCCL send/recv over NVLink on GPUs; gloo in the CPU tests).  48 exchanges per forward for Ours-s, 14.7 MB each
-at 720p level 1.  Supported for the nets whose roll wraps around the clip (Ours-s deblur, gshift_deblur2.py:504-505): the ring of
-ranks closes the wrap.
+at 720p level 1.  Where the roll wraps around the clip (Ours-s deblur, gshift_deblur2.py:504-505) the ring of ranks closes the wrap;
+where it clamps at the clip ends (the other nets, gshift_deblur1.py:513,517) the chain stays open and the two end ranks run their
+boundary step with the clamped rule.  gshift_denoise1 is not covered (its Shift_CABs roll outside the shift blocks).
 
 The halo frame is stored BEHIND the rank's own frames, at index Tl of a (Tl+1)-frame buffer: with the kernels' circular
 indexing over Tl+1 frames, frame 0's predecessor is index Tl and frame Tl-1's successor is index Tl, so the unmodified
@@ -37,38 +38,59 @@ class TShard:
     def n_local(self):
         return self.b - self.a
 
-    def exchange(self, send: torch.Tensor, reverse: bool) -> torch.Tensor:
-        """Ring exchange of one contiguous halo tensor.  forward pairs: every rank sends to rank+1 and receives from rank-1;
-        reverse pairs: sends to rank-1, receives from rank+1.  Returns the received tensor (same shape / dtype)."""
+    def needs_halo(self, reverse: bool, circular: bool) -> bool:
+        """Does this rank's CAB2 step of the given direction read a neighbour's frame?  Always with the wrapping roll; with the
+        clamped roll (gshift_deblur1.py:513,517) the first rank's forward step / the last rank's reverse step keep their boundary
+        frame un-swapped instead."""
+        if circular:
+            return True
+        return self.rank < self.world - 1 if reverse else self.rank > 0
+
+    def exchange(self, send: torch.Tensor, reverse: bool, circular: bool = True):
+        """Exchange of one contiguous halo tensor along the chain of ranks (a ring when the roll wraps).  forward pairs: every rank
+        sends to rank+1 and receives from rank-1; reverse pairs: sends to rank-1, receives from rank+1.  Returns the received
+        tensor (same shape / dtype), or None on a rank whose clip end clamps."""
         self.exchanges += 1
-        self.halo_bytes += send.numel() * send.element_size()
         if self.world == 1:
-            return send                                  # the ring of one rank: its own boundary frame is the wrap-around
+            self.halo_bytes += send.numel() * send.element_size() if circular else 0
+            return send if circular else None            # the ring of one rank: its own boundary frame is the wrap-around
         import torch.distributed as dist
-        dst = (self.rank + (-1 if reverse else 1)) % self.world
-        src = (self.rank + (1 if reverse else -1)) % self.world
-        recv = torch.empty_like(send)
+        dst = self.rank + (-1 if reverse else 1)
+        src = self.rank + (1 if reverse else -1)
+        if circular:
+            dst, src = dst % self.world, src % self.world
+        do_send, do_recv = 0 <= dst < self.world, 0 <= src < self.world
+        recv = torch.empty_like(send) if do_recv else None
         ev = None
         if self.time_exchanges and send.is_cuda:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        ops = [dist.P2POp(dist.isend, send, dst, self.group), dist.P2POp(dist.irecv, recv, src, self.group)]
-        for w in dist.batch_isend_irecv(ops):
+        ops = []
+        if do_send:
+            self.halo_bytes += send.numel() * send.element_size()
+            ops.append(dist.P2POp(dist.isend, send, dst, self.group))
+        if do_recv:
+            ops.append(dist.P2POp(dist.irecv, recv, src, self.group))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
             w.wait()
         if ev is not None:
             ev[1].record()
             self.events.append(ev)
         return recv
 
-    def halo_into(self, full: torch.Tensor, n: int, reverse: bool) -> None:
+    def halo_into(self, full: torch.Tensor, n: int, reverse: bool, circular: bool = True) -> None:
         """full: (n+1, H, W, C) NHWC buffer holding this rank's n frames in [:n]; fills the half of frame n that the CAB2 of the
         given direction reads from the neighbour: forward -> channels [C/2, C) of the previous rank's LAST frame,
         reverse -> channels [0, C/2) of the next rank's FIRST frame."""
         h = full.shape[-1] // 2
         if reverse:
-            full[n, :, :, :h] = self.exchange(full[0, :, :, :h].contiguous(), True)
+            got = self.exchange(full[0, :, :, :h].contiguous(), True, circular)
+            if got is not None:
+                full[n, :, :, :h] = got
         else:
-            full[n, :, :, h:] = self.exchange(full[n - 1, :, :, h:].contiguous(), False)
+            got = self.exchange(full[n - 1, :, :, h:].contiguous(), False, circular)
+            if got is not None:
+                full[n, :, :, h:] = got
 
     def local_output_range(self, past: int, future: int):
         """Own frames that survive the net's final crop of `past` / `future` context frames of the GLOBAL clip, as a local slice."""

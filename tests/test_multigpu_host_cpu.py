@@ -129,7 +129,15 @@ def _halo_worker(rank, world, port, q):
     fwd = full[n].clone()
     ts.halo_into(full, n, reverse=True)
     rev = full[n].clone()
-    q.put((rank, ts.a, ts.b, fwd[0, 0].tolist(), rev[0, 0].tolist(), ts.local_output_range(2, 2), ts.halo_bytes))
+    # the clamped roll: an open chain, the end ranks receive nothing for the step whose clip end they hold
+    full[n] = -1.0
+    ts.halo_into(full, n, reverse=False, circular=False)
+    cf = full[n, 0, 0].tolist()
+    full[n] = -1.0
+    ts.halo_into(full, n, reverse=True, circular=False)
+    cr = full[n, 0, 0].tolist()
+    q.put((rank, ts.a, ts.b, fwd[0, 0].tolist(), rev[0, 0].tolist(), ts.local_output_range(2, 2), ts.halo_bytes, cf, cr,
+           (ts.needs_halo(False, False), ts.needs_halo(True, False))))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -149,11 +157,13 @@ def test_tshard_halo_ring_gloo_world3():
     spans = [(g[1], g[2]) for g in got]
     assert spans == [(0, 4), (4, 8), (8, 11)]
     kept = 0
-    for rank, a, b, fwd, rev, (lo, hi), nbytes in got:
+    for rank, a, b, fwd, rev, (lo, hi), nbytes, cf, cr, need in got:
         prev_last, next_first = (a - 1) % T, b % T
         assert fwd[C // 2:] == [100.0 * prev_last + c for c in range(C // 2, C)]          # forward: high half of frame a-1
         assert rev[:C // 2] == [100.0 * next_first + c for c in range(C // 2)]             # reverse: low half of frame b
-        assert nbytes == 2 * (2 * 3 * C // 2) * 4
+        assert need == (rank > 0, rank < world - 1)
+        assert cf[C // 2:] == ([100.0 * (a - 1) + c for c in range(C // 2, C)] if rank > 0 else [-1.0] * (C // 2))
+        assert cr[:C // 2] == ([100.0 * b + c for c in range(C // 2)] if rank < world - 1 else [-1.0] * (C // 2))
         kept += hi - lo
         assert [a + i for i in range(lo, hi)] == [f for f in range(a, b) if 2 <= f < T - 2]
     assert kept == T - 4
