@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s -k "temporal_roll or (shift_block and deblur1) or (shift_block and denoise1) or pw_gate or ln_pw or conv3x3 or (gated_cab and deblur1) or (gated_cab and denoise1) or (golden and denoise1) or (tfr and deblur1) or (tfr and denoise1) or K3 or (golden and deblur1) or K5shape" > gpurun_out/c3_test.log 2>&1; echo "pytest exit $?" >> gpurun_out/c3_test.log
+timeout 900 python -m pytest tests -m gpu -x -q -s -k "conv3x3 or (shift_block and denoise1) or pw_gate or ln_pw or conv3x3 or (gated_cab and deblur1) or (gated_cab and denoise1) or (golden and denoise1) or (tfr and deblur1) or (tfr and denoise1) or K3 or (golden and deblur1) or K5shape" > gpurun_out/c3_test.log 2>&1; echo "pytest exit $?" >> gpurun_out/c3_test.log
 grep -E "conv3x3|parity-at-size|TFR|passed|failed|Error|error|exit" gpurun_out/c3_test.log | head -30
 if grep -q "pytest exit 0" gpurun_out/c3_test.log; then
   for tc in 1; do

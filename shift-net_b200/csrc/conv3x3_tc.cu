@@ -113,18 +113,18 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_tc_kernel(const __grid_
         mbar_wait(tmem_empty(acc), aph ^ 1);
         mbar_wait(full(s), ph);
         tc_fence_after();
+        // tap-major order: the four slabs' MMAs of one (tap, k-step) go out back to back -- four independent accumulators in flight
+        // (consecutive MMAs into ONE accumulator issue ~90 cycles apart here) and the same B operand four times in a row
 #pragma unroll 1
-        for (int mt = 0; mt < 4; ++mt) {
-          bool first = true;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int off = mt * 128 + (tap / 3) * K::RW + (tap % 3);      // region pixel of raster pixel 0 of the slab for this tap
+        for (int tap = 0; tap < 9; ++tap) {
+          const int toff = (tap / 3) * K::RW + (tap % 3);
 #pragma unroll
-            for (int k = 0; k < K::KC / 2; ++k) {
-              const uint64_t ad = smem_desc_at(sbase >> 4, s * K::STAGE + 2 * k * K::PLANE + off * 16, K::PLANE, 128);
-              const uint64_t bd = smem_desc_at(sbase >> 4, K::S_W + (tap * K::KC + 2 * k) * (K::NP * 16), K::NP * 16, 128);
-              umma_f16(tmem + acc * 256 + mt * 64, ad, bd, idesc, first ? 0u : 1u);
-              first = false;
+          for (int k = 0; k < K::KC / 2; ++k) {
+            const uint64_t bd = smem_desc_at(sbase >> 4, K::S_W + (tap * K::KC + 2 * k) * (K::NP * 16), K::NP * 16, 128);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              const uint64_t ad = smem_desc_at(sbase >> 4, s * K::STAGE + 2 * k * K::PLANE + (mt * 128 + toff) * 16, K::PLANE, 128);
+              umma_f16(tmem + acc * 256 + mt * 64, ad, bd, idesc, (tap | k) ? 1u : 0u);
             }
           }
         }
