@@ -21,7 +21,8 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))   # a mismatched exchange must fail fast, not hang
 T, H, W = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 256, 448)))
 ARCH = sys.argv[4] if len(sys.argv) > 4 else "gshift_deblur2"
 sd, spec = gio.synthetic_checkpoint(ARCH)

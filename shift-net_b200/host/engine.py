@@ -397,9 +397,13 @@ class Engine:
     def shift_cab(self, p, x, c, reverse):
         """Shift_CAB of Ours+ denoise (gshift_denoise1.py:157-186): clamped temporal roll, then the CAB body."""
         T, H, W, cp = x.shape
-        y = self._new(T, H, W, cp)
-        L.check(self.lib.gsn_roll_copy(x.data_ptr(), y.data_ptr(), T, H, W, c, cp, 1 if reverse else 0, self._stream()), "roll_copy")
-        return self.cab(p, y, c)
+        own = slice(0, T)
+        if self.tshard is not None:     # T-sharded clip: the neighbour rank's boundary frame joins the roll (host/tshard.py)
+            x, own = self.tshard.with_neighbour_frame(x, reverse, self._new)
+        n = x.shape[0]
+        y = self._new(n, H, W, cp)
+        L.check(self.lib.gsn_roll_copy(x.data_ptr(), y.data_ptr(), n, H, W, c, cp, 1 if reverse else 0, self._stream()), "roll_copy")
+        return self.cab(p, y[own], c)
 
     def gated_cab(self, p, x, mode, debug_stage=0, a1_pre=None, next_p=None):
         """One CAB2 (mode fwd/rev: shift folded into the load) or CAB1 step: pass A -> fold -> pass B.
@@ -604,8 +608,6 @@ class Engine:
             raise ValueError(f"H and W must be multiples of {m} for {sp.name} (got {H}x{W}); the reference scripts crop/pad to that")
         ts = self.tshard
         if ts is not None:
-            if sp.plus and sp.denoise:
-                raise ValueError("T-sharded mode does not cover gshift_denoise1 (its Shift_CABs roll outside the shift blocks)")
             if T != ts.n_local:
                 raise ValueError(f"T-sharded mode: this rank owns {ts.n_local} frames, got {T}")
             lo, hi = ts.local_output_range(past, future)

@@ -7,7 +7,8 @@ Each rank therefore needs, before every CAB2, ONE boundary frame's half of the c
 exchange below (NCCL send/recv over NVLink on GPUs; gloo in the CPU tests).  48 exchanges per forward for Ours-s, 14.7 MB each
 at 720p level 1.  Where the roll wraps around the clip (Ours-s deblur, gshift_deblur2.py:504-505) the ring of ranks closes the wrap;
 where it clamps at the clip ends (the other nets, gshift_deblur1.py:513,517) the chain stays open and the two end ranks run their
-boundary step with the clamped rule.  gshift_denoise1 is not covered (its Shift_CABs roll outside the shift blocks).
+boundary step with the clamped rule.  The four Shift_CABs of gshift_denoise1's encoder (gshift_denoise1.py:167-186) roll whole
+feature frames the same way and exchange one full boundary frame each (Engine.shift_cab).
 
 The halo frame is stored BEHIND the rank's own frames, at index Tl of a (Tl+1)-frame buffer: with the kernels' circular
 indexing over Tl+1 frames, frame 0's predecessor is index Tl and frame Tl-1's successor is index Tl, so the unmodified
@@ -49,7 +50,8 @@ class TShard:
     def exchange(self, send: torch.Tensor, reverse: bool, circular: bool = True):
         """Exchange of one contiguous halo tensor along the chain of ranks (a ring when the roll wraps).  forward pairs: every rank
         sends to rank+1 and receives from rank-1; reverse pairs: sends to rank-1, receives from rank+1.  Returns the received
-        tensor (same shape / dtype), or None on a rank whose clip end clamps."""
+        tensor (same shape / dtype), or None on a rank whose clip end clamps.  COLLECTIVE: every rank of the group must call it for
+        every exchange point, also the end ranks that only send or only receive."""
         self.exchanges += 1
         if self.world == 1:
             self.halo_bytes += send.numel() * send.element_size() if circular else 0
@@ -91,6 +93,22 @@ class TShard:
             got = self.exchange(full[n - 1, :, :, h:].contiguous(), False, circular)
             if got is not None:
                 full[n, :, :, h:] = got
+
+    def with_neighbour_frame(self, x: torch.Tensor, reverse: bool, alloc=None):
+        """Whole-frame clamped roll across ranks (Shift_CAB.channel_shift, gshift_denoise1.py:167-179): x (n, H, W, C) are this
+        rank's frames.  COLLECTIVE.  Returns (xf, own): xf = x with the neighbour's boundary frame in FRONT (forward: the previous
+        rank's last frame) or BEHIND (reverse: the next rank's first frame) and own = the slice of xf / of the rolled result that
+        belongs to this rank; the clamped roll over xf's n+1 frames then gives every own frame its true neighbour.  On the rank that
+        holds the clip end of this direction nothing arrives and (x, slice(0, n)) comes back: its boundary frame clamps."""
+        n = x.shape[0]
+        got = self.exchange(x[0 if reverse else n - 1].contiguous(), reverse, False)
+        if got is None:
+            return x, slice(0, n)
+        xf = alloc(n + 1, *x.shape[1:]) if alloc is not None else torch.empty((n + 1,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        own = slice(0, n) if reverse else slice(1, n + 1)
+        xf[own].copy_(x)
+        xf[n if reverse else 0].copy_(got)
+        return xf, own
 
     def local_output_range(self, past: int, future: int):
         """Own frames that survive the net's final crop of `past` / `future` context frames of the GLOBAL clip, as a local slice."""

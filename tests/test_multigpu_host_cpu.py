@@ -177,3 +177,42 @@ def test_tshard_single_rank_ring_is_the_circular_wrap():
     assert full[5, 0, 0].tolist() == [-1, -1, 18, 19]          # high half of its own last frame (frame 4)
     ts.halo_into(full, 5, reverse=True)
     assert full[5, 0, 0].tolist() == [0, 1, 18, 19]            # low half of its own first frame
+
+
+def _frame_roll_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, gio.ROOT)
+    from oracle import shiftnet_oracle as O
+    T, C = 11, 8
+    ts = gio.pkg("host.tshard").TShard(rank, world, T)
+    g = torch.Generator().manual_seed(5)
+    glob = torch.randn(T, 2, 3, C, generator=g)                       # NHWC frames of the whole clip
+    ok = []
+    for reverse in (False, True):
+        want = O.temporal_roll(glob.permute(0, 3, 1, 2), reverse, circular=False)[0].permute(0, 2, 3, 1)[ts.a:ts.b]
+        xf, own = ts.with_neighbour_frame(glob[ts.a:ts.b].contiguous(), reverse)
+        have = O.temporal_roll(xf.permute(0, 3, 1, 2), reverse, circular=False)[0].permute(0, 2, 3, 1)[own]
+        ok.append((bool(torch.equal(have, want)), xf.shape[0] - ts.n_local))
+    q.put((rank, ok, ts.exchanges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tshard_whole_frame_roll_of_shift_cab_gloo_world3():
+    """gshift_denoise1's Shift_CABs (gshift_denoise1.py:167-179) in T-sharded mode: TShard.with_neighbour_frame puts the neighbour
+    rank's boundary frame next to the own frames so that the clamped roll over n+1 frames equals the roll of the whole clip; the end
+    rank of each direction gets nothing and clamps.  Every rank calls the exchange (a rank that skipped it would deadlock NCCL)."""
+    world = 3
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_frame_roll_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    for rank, ok, nex in got:
+        assert nex == 2
+        assert ok[0] == (True, 1 if rank > 0 else 0)                  # forward: everyone but the first rank receives a frame
+        assert ok[1] == (True, 1 if rank < world - 1 else 0)          # reverse: everyone but the last rank
