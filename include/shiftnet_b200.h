@@ -165,13 +165,21 @@ int gsn_add(const void *a, const void *b, void *out, long long n, void *stream);
 #define GSN_MODE_CAB1 0
 #define GSN_MODE_CAB2_FWD 1
 #define GSN_MODE_CAB2_REV 2
+/* Values of every `circular` argument / field below: how the half-channel temporal roll treats the ends of the frame range.
+ *   GSN_ROLL_CLAMP  the first (forward) / last (reverse) frame stays un-swapped (gshift_deblur1.py:513,517)
+ *   GSN_ROLL_WRAP   the roll wraps around the T frames (gshift_deblur2.py:504-505)
+ *   GSN_ROLL_HALO   T-sharded clip (no reference counterpart): x holds T + 1 frames, frame T being the neighbour rank's boundary
+ *                   frame; the roll wraps over T + 1 frames while only the T own frames are computed and written */
+#define GSN_ROLL_CLAMP 0
+#define GSN_ROLL_WRAP 1
+#define GSN_ROLL_HALO 2
 /* GsnCabPassA.debug_stage value that routes the call to the row-streaming pass-A kernel whatever GSN_PASS_A_STREAM says */
 #define GSN_PASS_A_FORCE_STREAM 100
 
 typedef struct {
   int T, H, W, C;       /* C = 64 (Ours-s); activations (T,H,W,C) NHWC fp16 */
   int mode;             /* GSN_MODE_* */
-  int circular;         /* temporal roll wraps (d2:504-505) or clamps (gshift_deblur1.py:513,517) */
+  int circular;         /* GSN_ROLL_*: temporal roll wraps (d2:504-505), clamps (gshift_deblur1.py:513,517) or reads a halo frame */
   const void *x;        /* input of the step (un-rolled previous output) */
   const void *wblob;    /* packed pass-A weights, see host/packing.py (pack_cab_pass_a) */
   void *z;              /* out: gated features (T,H,W,C) fp16 */

@@ -167,7 +167,7 @@ int cab_pass_b80_tc_dispatch(const GsnCabPassB &d, cudaStream_t st) {
   CUtensorMap tm_z, tm_x;
   memset(&tm_z, 0, sizeof(tm_z));
   memset(&tm_x, 0, sizeof(tm_x));
-  if (!encode_tmap_chunk128(&tm_z, d.z, 80, hw, d.T) || !encode_tmap_chunk128(&tm_x, d.x, 80, hw, d.T)) {
+  if (!encode_tmap_chunk128(&tm_z, d.z, 80, hw, d.T) || !encode_tmap_chunk128(&tm_x, d.x, 80, hw, roll_frames(d.circular, d.T))) {
     set_error("cab_pass_b (C=80): cuTensorMapEncodeTiled failed (H*W=%lld T=%d)", hw, d.T);
     return GSN_E_CUDA;
   }

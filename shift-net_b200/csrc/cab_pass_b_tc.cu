@@ -258,7 +258,7 @@ int cab_pass_b_tc_dispatch(const GsnCabPassB &d, cudaStream_t st) {
   memset(&tm_x, 0, sizeof(tm_x));
   memset(&tm_out, 0, sizeof(tm_out));
   if (!encode_tmap_pix(&tm_z, d.z, 64, hw, d.T, 64, K::MP, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !encode_tmap_pix(&tm_x, d.x, 64, hw, d.T, 32, K::MP, CU_TENSOR_MAP_SWIZZLE_64B) ||
+      !encode_tmap_pix(&tm_x, d.x, 64, hw, roll_frames(d.circular, d.T), 32, K::MP, CU_TENSOR_MAP_SWIZZLE_64B) ||
       !encode_tmap_pix(&tm_out, d.out, 64, hw, d.T, 64, K::MP, CU_TENSOR_MAP_SWIZZLE_128B)) {
     set_error("cab_pass_b: cuTensorMapEncodeTiled failed (H*W=%lld T=%d)", hw, d.T);
     return GSN_E_CUDA;

@@ -715,7 +715,7 @@ extern "C" int gsn_shift_conv1(const void *x, int T, int H, int W, int C, int mo
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   bool tma_ok = false;
-  if (use_tma) tma_ok = encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34);
+  if (use_tma) tma_ok = encode_tmap_nhwc(&tm, x, C, W, H, roll_frames(circular, T), C / 2, 34, 34);
   const __half *xh = reinterpret_cast<const __half *>(x), *wh = reinterpret_cast<const __half *>(wc1);
   __half *oh = reinterpret_cast<__half *>(out);
   if (C == 64) {
@@ -740,7 +740,7 @@ extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int
   GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(shift_conv1_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  if (!encode_tmap_nhwc(&tm, x, C, W, H, T, C / 2, 34, 34)) {
+  if (!encode_tmap_nhwc(&tm, x, C, W, H, roll_frames(circular, T), C / 2, 34, 34)) {
     set_error("shift_conv1_ln: cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", W, H, T);
     return GSN_E_CUDA;
   }
@@ -750,7 +750,7 @@ extern "C" int gsn_shift_conv1_ln(const void *x, int T, int H, int W, int C, int
     GSN_ONCE_PER_DEVICE(cudaFuncSetAttribute(shift_conv1_ln_h8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
     CUtensorMap tm8;
     memset(&tm8, 0, sizeof(tm8));
-    if (!encode_tmap_nhwc(&tm8, x, C, W, H, T, C / 2, 34, 26)) {
+    if (!encode_tmap_nhwc(&tm8, x, C, W, H, roll_frames(circular, T), C / 2, 34, 26)) {
       set_error("shift_conv1_ln: cuTensorMapEncodeTiled failed (W=%d H=%d T=%d)", W, H, T);
       return GSN_E_CUDA;
     }

@@ -228,7 +228,7 @@ extern "C" int gsn_ln_pw_tc(const void *x, const void *hw_pre, int T, int H, int
   CUtensorMap tm_x, tm_hw;
   memset(&tm_x, 0, sizeof(tm_x));
   memset(&tm_hw, 0, sizeof(tm_hw));
-  if (!encode_tmap_chunk128(&tm_x, x, C, hw, T) || (hw_pre && !encode_tmap_chunk128(&tm_hw, hw_pre, C / 2, hw, T))) {
+  if (!encode_tmap_chunk128(&tm_x, x, C, hw, roll_frames(circular, T)) || (hw_pre && !encode_tmap_chunk128(&tm_hw, hw_pre, C / 2, hw, T))) {
     set_error("ln_pw_tc: cuTensorMapEncodeTiled failed (H*W=%lld T=%d)", hw, T);
     return GSN_E_CUDA;
   }

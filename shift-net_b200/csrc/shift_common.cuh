@@ -42,15 +42,18 @@ inline ShiftTable make_shift_table(int C) {
 struct RollSrc {
   int f_lo, c_lo, f_hi, c_hi;
 };
+// Frames of the rolled source tensor x: T, or T + 1 with GSN_ROLL_HALO (a T-sharded clip: the neighbour rank's boundary frame is
+// stored behind the T own frames, at index T, and is reached by wrapping; only the T own frames are computed).
+__host__ __device__ inline int roll_frames(int circular, int T) { return circular == GSN_ROLL_HALO ? T + 1 : T; }
 __host__ __device__ inline RollSrc roll_source(int mode, int circular, int t, int T, int C) {
   RollSrc r;
-  const int h = C / 2;
+  const int h = C / 2, R = roll_frames(circular, T);
   if (mode == GSN_MODE_CAB2_FWD) {
     if (!circular && t == 0) { r.f_lo = 0; r.c_lo = 0; r.f_hi = 0; r.c_hi = h; }
-    else { r.f_lo = (t + T - 1) % T; r.c_lo = h; r.f_hi = t; r.c_hi = 0; }
+    else { r.f_lo = (t + R - 1) % R; r.c_lo = h; r.f_hi = t; r.c_hi = 0; }
   } else if (mode == GSN_MODE_CAB2_REV) {
     if (!circular && t == T - 1) { r.f_lo = t; r.c_lo = 0; r.f_hi = t; r.c_hi = h; }
-    else { r.f_lo = t; r.c_lo = h; r.f_hi = (t + 1) % T; r.c_hi = 0; }
+    else { r.f_lo = t; r.c_lo = h; r.f_hi = (t + 1) % R; r.c_hi = 0; }
   } else { r.f_lo = t; r.c_lo = 0; r.f_hi = t; r.c_hi = h; }
   return r;
 }

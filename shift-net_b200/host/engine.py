@@ -485,8 +485,8 @@ class Engine:
             fuse = self.ln_fuse and x.shape[-1] == 64
             rev = bool(i & 1)
             if ts is not None:
-                # this rank's n frames + the neighbour's boundary frame behind them (host/tshard.py): the kernels' circular indexing
-                # over n+1 frames then finds frame 0's predecessor / frame n-1's successor at index n.  For the nets whose roll CLAMPS
+                # this rank's n frames + the neighbour's boundary frame behind them (host/tshard.py): the kernels' roll over n+1 frames
+                # (GSN_ROLL_HALO) finds frame 0's predecessor / frame n-1's successor at index n.  For the nets whose roll CLAMPS
                 # at the ends of the clip, the rank that holds that end runs the step on its n frames with the clamped rule (it still
                 # serves its other neighbour in the exchange).
                 n = x.shape[0]
@@ -496,14 +496,13 @@ class Engine:
                     full = self._new(n + 1, *x.shape[1:])
                     full[:n].copy_(x)
                 ts.halo_into(full, n, rev, circular=self.spec.circular)
-                self._circ_override = 1 if use_halo else 0
+                # the kernels compute the n own frames; with ROLL_HALO their roll reaches frame n of the same buffer
+                self._circ_override = L.ROLL_HALO if use_halo else L.ROLL_CLAMP
                 try:
-                    y = self.gated_cab(q + ".0", full if use_halo else full[:n], L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD,
-                                       next_p=(q + ".1") if fuse else None)
+                    y = self.gated_cab(q + ".0", full[:n], L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
                 finally:
                     self._circ_override = None
-                a1 = self._a1_next[:n] if (fuse and self._a1_next is not None) else None   # planar operand is frame-major: prefix view
-                x = self.gated_cab(q + ".1", y[:n], L.MODE_CAB1, a1_pre=a1)
+                x = self.gated_cab(q + ".1", y, L.MODE_CAB1, a1_pre=self._a1_next if fuse else None)
                 continue
             x = self.gated_cab(q + ".0", x, L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD, next_p=(q + ".1") if fuse else None)
             x = self.gated_cab(q + ".1", x, L.MODE_CAB1, a1_pre=self._a1_next if fuse else None)

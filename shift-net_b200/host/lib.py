@@ -21,6 +21,7 @@ EXPORTS = [
 MODE_CAB1, MODE_CAB2_FWD, MODE_CAB2_REV = 0, 1, 2
 DTYPE_F16, DTYPE_F32 = 0, 1
 PASS_A_FORCE_STREAM = 100      # GsnCabPassA.debug_stage: GSN_PASS_A_FORCE_STREAM
+ROLL_CLAMP, ROLL_WRAP, ROLL_HALO = 0, 1, 2      # include/shiftnet_b200.h GSN_ROLL_*
 
 
 class ConvDesc(C.Structure):

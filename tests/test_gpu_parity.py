@@ -243,6 +243,28 @@ def test_gated_cab(aenv, which, circular):
         check(out, torch.from_numpy(gold[which]), 3e-3, f"{which} vs reference golden")
 
 
+@pytest.mark.parametrize("rev", [False, True])
+def test_gated_cab_roll_halo_equals_wrap_over_one_more_frame(aenv, rev):
+    """GSN_ROLL_HALO (T-sharded clips, include/shiftnet_b200.h): CAB2 on the n own frames of an (n+1)-frame buffer, the roll reaching
+    frame n by wrapping, must equal -- bit for bit -- the first n frames of the wrapping CAB2 over all n+1 frames.  All four nets
+    (the C=64 fused kernels and the C=80 TMA/tcgen05 kernels build their tensor maps over n+1 frames)."""
+    sd, spec, eng, _ = aenv
+    L = gio.pkg("host.lib")
+    g = torch.Generator().manual_seed(11)
+    n = 3
+    full = to_nhwc(0.5 * torch.randn(n + 1, spec.c1, 40, 56, generator=g))
+    p = "stage1.decoder_level1" + (".encoder_level1_1.0" if rev else ".encoder_level1.0")
+    mode = L.MODE_CAB2_REV if rev else L.MODE_CAB2_FWD
+    try:
+        eng._circ_override = L.ROLL_WRAP
+        want = eng.gated_cab(p, full, mode)[:n].clone()
+        eng._circ_override = L.ROLL_HALO
+        have = eng.gated_cab(p, full[:n], mode)
+    finally:
+        eng._circ_override = None
+    assert have.shape == want.shape and torch.equal(have, want)
+
+
 def test_gated_cab_ragged_sizes(env):
     """H, W not multiples of the tile, T=1 and T=2 (wrap onto itself / neighbour is the only other frame)."""
     sd, spec, eng, _ = env
