@@ -10,9 +10,9 @@ where it clamps at the clip ends (the other nets, gshift_deblur1.py:513,517) the
 boundary step with the clamped rule.  The four Shift_CABs of gshift_denoise1's encoder (gshift_denoise1.py:167-186) roll whole
 feature frames the same way and exchange one full boundary frame each (Engine.shift_cab).
 
-The halo frame is stored BEHIND the rank's own frames, at index Tl of a (Tl+1)-frame buffer: with the kernels' circular
-indexing over Tl+1 frames, frame 0's predecessor is index Tl and frame Tl-1's successor is index Tl, so the unmodified
-single-GPU kernels compute every own frame correctly (the halo frame's own output is discarded).
+The halo frame is stored BEHIND the rank's own frames, at index Tl of a (Tl+1)-frame buffer, and the CAB2 kernels run on the Tl
+own frames with circular = GSN_ROLL_HALO (include/shiftnet_b200.h): their roll wraps over Tl+1 frames, so frame 0's predecessor is
+index Tl and frame Tl-1's successor is index Tl; nothing is computed for the halo frame.
 """
 from __future__ import annotations
 
