@@ -292,7 +292,7 @@ def run_strong(args, net, spec, rank, world, dev, dist):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": f"{args.arch} synthetic {Hh}x{Ww} one_len={out_frames}, ONE clip (1,{Tn},3,{Hh},{Ww}) T-sharded over {world} rank(s)",
-                       "sharding": f"frames of one clip x{world} (rank 0 owns {ts.n_local}), halo exchange before every CAB2, eager launches",
+                       "sharding": f"frames of one clip x{world} (rank 0 owns {ts.n_local}), halo exchange before every CAB2, " + ("CUDA graphs cut at the exchanges, NCCL between them" if (world > 1 and os.environ.get("GSN_TSHARD_GRAPH", "1") != "0" and os.environ.get("GSN_CUDA_GRAPH", "1") != "0") else "eager launches"),
                        "l2": "activations larger than L2, no flush needed", "accumulate": "fp32", "storage": "fp16 NHWC"},
             "e2e": {"value": out_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * 2 * world,
                     "d2h_bytes_per_step": out_frames * 3 * Hh * Ww * 2, "ms_per_step": ms_e2e},

@@ -89,12 +89,53 @@ class GShiftNetB200(nn.Module):
     @torch.no_grad()
     def forward_tsharded(self, x_local, tshard, noise_map=None):
         """One slice of a T-sharded clip (host/tshard.py): x_local (1, n_local, 3, H, W) are the frames this rank owns (noise_map
-        (1, n_local, 1, H, W) for the denoise nets); returns the
-        restored frames among them (the clip's context frames are cropped on the ranks that hold them).  Launches eagerly: the
-        halo exchanges are NCCL point-to-point operations between the kernels."""
+        (1, n_local, 1, H, W) for the denoise nets); returns the restored frames among them (the clip's context frames are cropped
+        on the ranks that hold them).  COLLECTIVE over the ranks of `tshard`.  With more than one rank the forward is replayed as a
+        chain of CUDA graphs cut at the halo exchanges (host/tshard.py SegmentedGraph; GSN_TSHARD_GRAPH=0 or GSN_CUDA_GRAPH=0
+        launch eagerly); the NCCL point-to-point calls run between the graphs."""
         if not x_local.is_cuda:
             raise RuntimeError("shiftnet_b200.GShiftNet runs on CUDA (B200, sm_100a) only; there is no CPU fallback")
         eng = self.engine()
+        lib = eng.lib
+        import os
+        graphed = (self.use_cuda_graph and tshard.world > 1 and os.environ.get("GSN_TSHARD_GRAPH", "1") != "0"
+                   and eng.timeline is None and not torch.cuda.is_current_stream_capturing())
+        if not graphed:
+            return self._tsharded_eager(eng, x_local, tshard, noise_map)
+        key = ("tshard", tuple(x_local.shape), x_local.dtype, None if noise_map is None else tuple(noise_map.shape), self.num_fb,
+               self.num_ff, tshard.rank, tshard.world, tshard.T)
+        ent = self._graphs.get(key)
+        if ent is None or ent[0].ts is not tshard:
+            from .tshard import SegmentedGraph
+            xs = x_local.clone()
+            ns = None if noise_map is None else noise_map.expand(noise_map.shape).clone()
+            self._tsharded_eager(eng, xs, tshard, ns)          # eager warm-up, halo exchanges included: packs weights, primes the allocator
+            torch.cuda.synchronize(x_local.device)
+            seg = SegmentedGraph(tshard)
+            side = torch.cuda.Stream(x_local.device)
+            side.wait_stream(torch.cuda.current_stream(x_local.device))
+            eng.tshard, tshard.recorder = tshard, seg
+            l0 = lib.gsn_launch_count()
+            try:
+                with torch.cuda.stream(side):
+                    seg.begin()
+                    out_s = eng.forward(xs, ns, past=self.num_fb, future=self.num_ff)
+                    seg.end()
+            finally:
+                eng.tshard, tshard.recorder = None, None
+            torch.cuda.current_stream(x_local.device).wait_stream(side)
+            torch.cuda.synchronize(x_local.device)
+            ent = (seg, xs, ns, out_s, lib.gsn_launch_count() - l0)
+            self._graphs = {key: ent}
+        seg, xs, ns, out_s, n_kernels = ent
+        xs.copy_(x_local)
+        if ns is not None:
+            ns.copy_(noise_map)
+        seg.replay()
+        self.kernel_launches += n_kernels
+        return out_s.clone()
+
+    def _tsharded_eager(self, eng, x_local, tshard, noise_map):
         lib = eng.lib
         eng.tshard = tshard
         try:

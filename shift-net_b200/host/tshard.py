@@ -34,6 +34,7 @@ class TShard:
         self.exchanges = 0
         self.events = []             # (start, end) CUDA event pairs around the exchanges, when timing is on
         self.time_exchanges = False
+        self.recorder = None         # a SegmentedGraph during its capture pass
 
     @property
     def n_local(self):
@@ -56,29 +57,36 @@ class TShard:
         if self.world == 1:
             self.halo_bytes += send.numel() * send.element_size() if circular else 0
             return send if circular else None            # the ring of one rank: its own boundary frame is the wrap-around
-        import torch.distributed as dist
         dst = self.rank + (-1 if reverse else 1)
         src = self.rank + (1 if reverse else -1)
         if circular:
             dst, src = dst % self.world, src % self.world
-        do_send, do_recv = 0 <= dst < self.world, 0 <= src < self.world
-        recv = torch.empty_like(send) if do_recv else None
+        dst = dst if 0 <= dst < self.world else None
+        src = src if 0 <= src < self.world else None
+        if self.recorder is not None:        # capture pass of a SegmentedGraph: the launches so far become one CUDA graph
+            return self.recorder.cut(send, dst, src)
+        recv = torch.empty_like(send) if src is not None else None
+        self._p2p(send, recv, dst, src)
+        return recv
+
+    def _p2p(self, send, recv, dst, src):
+        """One point-to-point step on the current stream: send -> rank dst, recv <- rank src (either may be None)."""
+        import torch.distributed as dist
         ev = None
         if self.time_exchanges and send.is_cuda:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         ops = []
-        if do_send:
+        if dst is not None:
             self.halo_bytes += send.numel() * send.element_size()
             ops.append(dist.P2POp(dist.isend, send, dst, self.group))
-        if do_recv:
+        if src is not None:
             ops.append(dist.P2POp(dist.irecv, recv, src, self.group))
         for w in (dist.batch_isend_irecv(ops) if ops else []):
             w.wait()
         if ev is not None:
             ev[1].record()
             self.events.append(ev)
-        return recv
 
     def halo_into(self, full: torch.Tensor, n: int, reverse: bool, circular: bool = True) -> None:
         """full: (n+1, H, W, C) NHWC buffer holding this rank's n frames in [:n]; fills the half of frame n that the CAB2 of the
@@ -115,3 +123,42 @@ class TShard:
         lo = max(past - self.a, 0)
         hi = self.n_local - max(self.b - (self.T - future), 0)
         return lo, max(hi, lo)
+
+
+class SegmentedGraph:
+    """One T-sharded forward as a chain of CUDA graphs cut at the halo exchanges: the ~3 400 kernel launches of a forward replay as
+    ~50 graph launches, and the NCCL point-to-point calls run eagerly between them on static send / receive buffers.  (The eager
+    T-sharded path is host-launch-bound from two ranks on; NCCL calls stay outside the graphs on purpose.)  All segments share one
+    memory pool and are replayed in capture order, so tensors that live across an exchange keep their addresses."""
+
+    def __init__(self, ts: TShard):
+        self.ts = ts
+        self.graphs, self.cuts = [], []
+        self.pool = torch.cuda.graph_pool_handle()
+        self.cur = None
+
+    def begin(self):
+        self.cur = torch.cuda.CUDAGraph()
+        self.cur.capture_begin(pool=self.pool, capture_error_mode="thread_local")   # the NCCL watchdog thread keeps polling its events
+
+    def cut(self, send, dst, src):
+        """Called by TShard.exchange during the capture pass: close the running segment, reserve the receive buffer, open the next."""
+        self.cur.capture_end()
+        self.graphs.append(self.cur)
+        recv = torch.empty_like(send) if src is not None else None
+        self.cuts.append((send, recv, dst, src))
+        self.begin()
+        return recv
+
+    def end(self):
+        self.cur.capture_end()
+        self.graphs.append(self.cur)
+        self.cur = None
+
+    def replay(self):
+        ts = self.ts
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if i < len(self.cuts):
+                ts.exchanges += 1
+                ts._p2p(*self.cuts[i])
