@@ -216,3 +216,76 @@ def test_tshard_whole_frame_roll_of_shift_cab_gloo_world3():
         assert nex == 2
         assert ok[0] == (True, 1 if rank > 0 else 0)                  # forward: everyone but the first rank receives a frame
         assert ok[1] == (True, 1 if rank < world - 1 else 0)          # reverse: everyone but the last rank
+
+
+class _FakeGraph:
+    """Stands in for torch.cuda.CUDAGraph on CPU: records the order of capture / replay calls."""
+    log = []
+
+    def capture_begin(self, pool=None, capture_error_mode="global"):
+        _FakeGraph.log.append("begin")
+
+    def capture_end(self):
+        _FakeGraph.log.append("end")
+
+    def replay(self):
+        _FakeGraph.log.append("replay")
+
+
+def _segmented_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts_mod = gio.pkg("host.tshard")
+    torch.cuda.CUDAGraph, torch.cuda.graph_pool_handle = _FakeGraph, (lambda: 0)      # this process only
+    ts = ts_mod.TShard(rank, world, 9)
+    seg = ts_mod.SegmentedGraph(ts)
+    points = [(False, True), (True, True), (False, False), (True, False)]               # (reverse, circular) of four exchange points
+    # capture pass: no communication, every exchange cuts the segment and hands out a static receive buffer
+    ts.recorder = seg
+    seg.begin()
+    sends, recvs = [], []
+    for k, (rev, circ) in enumerate(points):
+        s = torch.full((2, 3), float(100 * rank + k))
+        sends.append(s)
+        recvs.append(ts.exchange(s, rev, circ))
+    seg.end()
+    ts.recorder = None
+    captured = list(_FakeGraph.log)
+    # replay twice with fresh data in the static send buffers
+    out = []
+    for it in range(2):
+        for k, s in enumerate(sends):
+            s.fill_(1000.0 * it + 100 * rank + k)
+        _FakeGraph.log.clear()
+        ts.exchanges = 0
+        seg.replay()
+        out.append([None if r is None else float(r[0, 0]) for r in recvs])
+    q.put((rank, captured, list(_FakeGraph.log), ts.exchanges, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_segmented_graph_cuts_at_every_exchange_and_replays_the_p2p_steps_gloo_world3():
+    """host/tshard.py SegmentedGraph (the T-sharded forward as CUDA graphs cut at the halo exchanges), protocol only, with stand-in
+    graph objects: the capture pass communicates nothing and cuts one segment per exchange on EVERY rank (also where a clamped
+    clip end neither sends nor receives); a replay runs graph, p2p, graph, p2p, ... in order and delivers the neighbour's current
+    send buffer into the static receive buffer."""
+    world = 3
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_segmented_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    for rank, captured, replayed, nex, out in got:
+        assert captured == ["begin"] + ["end", "begin"] * 4 + ["end"]
+        assert replayed == ["replay"] * 5 and nex == 4
+        for it in range(2):
+            base = 1000.0 * it
+            prev, nxt = (rank - 1) % world, (rank + 1) % world
+            want = [base + 100 * prev + 0,                                   # forward, ring: from rank-1
+                    base + 100 * nxt + 1,                                    # reverse, ring: from rank+1
+                    base + 100 * (rank - 1) + 2 if rank > 0 else None,       # forward, open chain
+                    base + 100 * (rank + 1) + 3 if rank < world - 1 else None]
+            assert out[it] == want, (rank, it, out[it], want)

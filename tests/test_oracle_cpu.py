@@ -132,6 +132,17 @@ def test_ctypes_structs_match_the_header(tmp_path):
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_python_constants_match_the_header():
+    """Modes, dtypes, roll rules and the kernel selector of host/lib.py are the header's #defines."""
+    lib_mod = importlib.import_module("shift-net_b200.host.lib")
+    header = open(os.path.join(gio.ROOT, "include", "shiftnet_b200.h")).read()
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"^#define\s+(GSN_[A-Z0-9_]+)\s+(-?\d+)\s*$", header, re.M)}
+    for py, c in (("MODE_CAB1", "GSN_MODE_CAB1"), ("MODE_CAB2_FWD", "GSN_MODE_CAB2_FWD"), ("MODE_CAB2_REV", "GSN_MODE_CAB2_REV"),
+                  ("ROLL_CLAMP", "GSN_ROLL_CLAMP"), ("ROLL_WRAP", "GSN_ROLL_WRAP"), ("ROLL_HALO", "GSN_ROLL_HALO"),
+                  ("PASS_A_FORCE_STREAM", "GSN_PASS_A_FORCE_STREAM")):
+        assert c in macros and getattr(lib_mod, py) == macros[c], (py, c)
+
+
 def test_product_path_never_imports_oracle():
     bad = []
     for d, _, files in os.walk(os.path.join(gio.ROOT, "shift-net_b200")):
