@@ -28,6 +28,10 @@ def split_frames(T: int, world: int, rank: int):
 
 class TShard:
     def __init__(self, rank: int, world: int, T_global: int, group=None):
+        if not (0 <= rank < world):
+            raise ValueError(f"rank {rank} outside a group of {world}")
+        if T_global < world:
+            raise ValueError(f"a clip of {T_global} frames cannot be T-sharded over {world} ranks (every rank needs at least one frame)")
         self.rank, self.world, self.T, self.group = rank, world, T_global, group
         self.a, self.b = split_frames(T_global, world, rank)
         self.halo_bytes = 0          # bytes this rank SENT in halo exchanges (statistics for bench.py)
@@ -120,7 +124,7 @@ class TShard:
 
     def local_output_range(self, past: int, future: int):
         """Own frames that survive the net's final crop of `past` / `future` context frames of the GLOBAL clip, as a local slice."""
-        lo = max(past - self.a, 0)
+        lo = min(max(past - self.a, 0), self.n_local)
         hi = self.n_local - max(self.b - (self.T - future), 0)
         return lo, max(hi, lo)
 

@@ -289,3 +289,30 @@ def test_segmented_graph_cuts_at_every_exchange_and_replays_the_p2p_steps_gloo_w
                     base + 100 * (rank - 1) + 2 if rank > 0 else None,       # forward, open chain
                     base + 100 * (rank + 1) + 3 if rank < world - 1 else None]
             assert out[it] == want, (rank, it, out[it], want)
+
+
+def test_tshard_frame_split_properties():
+    """split_frames / local_output_range over every (T, world) of interest: the ranks' ranges tile [0, T) in order, differ by at most
+    one frame, the frames that survive the crop of the 2 + 2 context frames are exactly [2, T-2) with no overlap, and the open
+    chain of a clamped roll has exactly world-1 receivers per direction."""
+    ts_mod = gio.pkg("host.tshard")
+    for world in range(1, 9):
+        for T in range(max(world, 5), 70):
+            shards = [ts_mod.TShard(r, world, T) for r in range(world)]
+            assert shards[0].a == 0 and shards[-1].b == T
+            assert all(shards[i].b == shards[i + 1].a for i in range(world - 1))
+            sizes = [s.n_local for s in shards]
+            assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+            kept = []
+            for s in shards:
+                lo, hi = s.local_output_range(2, 2)
+                assert 0 <= lo <= hi <= s.n_local
+                kept += [s.a + i for i in range(lo, hi)]
+            assert kept == list(range(2, T - 2))
+            for rev in (False, True):
+                assert sum(s.needs_halo(rev, False) for s in shards) == world - 1
+                assert all(s.needs_halo(rev, True) for s in shards)
+    with pytest.raises(ValueError):
+        ts_mod.TShard(0, 4, 3)
+    with pytest.raises(ValueError):
+        ts_mod.TShard(4, 4, 20)
